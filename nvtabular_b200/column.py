@@ -1,0 +1,304 @@
+"""Device column model: typed data + Arrow validity bitmask (+ list offsets,
++ string dictionary).  This replaces merlin.core.dispatch's DataFrameType
+(reference nvtabular/dispatch.py:21) for the hot path: kernels read these
+buffers through the C-ABI (include/nvtb200.h, nvtb_col_t).
+
+Host<->device conversion lives here and is NOT on the measured hot path; it
+uses torch only as a memory/stream provider.
+"""
+from typing import Dict, List, Optional
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _lib
+
+_TORCH2CODE = {
+    torch.int32: _lib.I32, torch.int64: _lib.I64, torch.float32: _lib.F32,
+    torch.float64: _lib.F64, torch.uint8: _lib.U8, torch.bool: _lib.U8,
+}
+_NP2TORCH = {
+    np.dtype("int32"): torch.int32, np.dtype("int64"): torch.int64,
+    np.dtype("float32"): torch.float32, np.dtype("float64"): torch.float64,
+    np.dtype("uint8"): torch.uint8, np.dtype("bool"): torch.bool,
+}
+_BIT_WEIGHTS = (1, 2, 4, 8, 16, 32, 64, 128)
+
+
+def default_device():
+    return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+
+
+def pack_validity(valid: torch.Tensor) -> torch.Tensor:
+    """bool[n] -> uint8[ceil(n/8)] bitmask, LSB-first (Arrow layout), padded to 32 B."""
+    n = valid.numel()
+    nbytes = (n + 7) // 8
+    padded = ((nbytes + 31) // 32) * 32
+    bits = torch.zeros(padded * 8, dtype=torch.uint8, device=valid.device)
+    bits[:n] = valid.to(torch.uint8)
+    w = torch.tensor(_BIT_WEIGHTS, dtype=torch.uint8, device=valid.device)
+    return (bits.view(-1, 8) * w).sum(dim=1, dtype=torch.int32).to(torch.uint8)
+
+
+def unpack_validity(mask: Optional[torch.Tensor], n: int, device=None) -> torch.Tensor:
+    """uint8 bitmask -> bool[n]."""
+    if mask is None:
+        return torch.ones(n, dtype=torch.bool, device=device)
+    w = torch.tensor(_BIT_WEIGHTS, dtype=torch.uint8, device=mask.device)
+    bits = (mask.view(-1, 1) & w) != 0
+    return bits.reshape(-1)[:n]
+
+
+class Column:
+    """One column resident in device memory.
+
+    data      : 1-D tensor (int32/int64/float32/float64/uint8); for a list
+                column the flattened leaf values; for a string column the
+                order-preserving dictionary codes.
+    validity  : uint8 bitmask (bit=1 -> non-null) or None
+    offsets   : int64[nrows+1] for list (multi-hot) columns, else None
+    dictionary: numpy object array of the sorted distinct strings, else None
+    fill      : a deferred FillMissing value (fused into the next kernel that
+                consumes the column), else None
+    """
+
+    __slots__ = ("data", "validity", "offsets", "dictionary", "fill", "is_bool")
+
+    def __init__(self, data, validity=None, offsets=None, dictionary=None, fill=None, is_bool=False):
+        if data.dtype == torch.bool:
+            data = data.to(torch.uint8)
+            is_bool = True
+        self.data = data
+        self.validity = validity
+        self.offsets = offsets
+        self.dictionary = dictionary
+        self.fill = fill
+        self.is_bool = is_bool
+
+    # ------------------------------------------------------------------ meta
+    @property
+    def nrows(self) -> int:
+        return int(self.offsets.numel() - 1) if self.offsets is not None else int(self.data.numel())
+
+    def __len__(self):
+        return self.nrows
+
+    @property
+    def is_list(self) -> bool:
+        return self.offsets is not None
+
+    @property
+    def is_string(self) -> bool:
+        return self.dictionary is not None
+
+    @property
+    def dtype_code(self) -> int:
+        return _TORCH2CODE[self.data.dtype]
+
+    @property
+    def np_dtype(self):
+        if self.is_string:
+            return np.dtype("object")
+        if self.is_bool:
+            return np.dtype("bool")
+        return np.dtype(str(self.data.dtype).replace("torch.", ""))
+
+    def desc(self):
+        """(data_ptr, validity_ptr|None, dtype_code) for _lib.col_array."""
+        return (self.data.data_ptr() if self.data.numel() else None,
+                self.validity.data_ptr() if self.validity is not None else None,
+                self.dtype_code)
+
+    def leaves(self) -> "Column":
+        """The flattened values of a list column (itself otherwise)."""
+        if not self.is_list:
+            return self
+        return Column(self.data, self.validity, None, self.dictionary, self.fill, self.is_bool)
+
+    def with_data(self, data, validity=None, keep_list=True) -> "Column":
+        return Column(data, validity, self.offsets if keep_list else None, None)
+
+    def null_count(self) -> int:
+        if self.validity is None:
+            return 0
+        n = self.data.numel()
+        return int(n - unpack_validity(self.validity, n).sum().item())
+
+    # ------------------------------------------------------------- host -> device
+    @classmethod
+    def from_numpy(cls, arr: np.ndarray, mask: Optional[np.ndarray] = None, device=None) -> "Column":
+        """arr: numeric ndarray; mask: bool ndarray, True = NULL (pandas convention)."""
+        device = device or default_device()
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype not in _NP2TORCH:
+            if np.issubdtype(arr.dtype, np.integer):
+                # small / unsigned ints widen to the next supported signed type
+                arr = arr.astype("int32" if arr.dtype.itemsize < 4 else "int64")
+            elif np.issubdtype(arr.dtype, np.floating):
+                arr = arr.astype("float32" if arr.dtype.itemsize < 4 else "float64")
+            else:
+                raise TypeError(f"unsupported column dtype {arr.dtype}")
+        t = torch.from_numpy(arr).to(device)
+        validity = None
+        if mask is not None and mask.any():
+            validity = pack_validity(torch.from_numpy(~np.asarray(mask, dtype=bool)).to(device))
+        return cls(t, validity)
+
+    @classmethod
+    def from_strings(cls, values, device=None) -> "Column":
+        """Dictionary-encode strings with ORDER-PRESERVING codes (code order ==
+        string order), so the (size desc, key asc) vocabulary rule holds on codes."""
+        device = device or default_device()
+        ser = pd.Series(values, dtype="object")
+        isnull = ser.isna().to_numpy()
+        uniq = np.array(sorted(set(ser[~isnull].tolist())), dtype=object)
+        lut = {s: i for i, s in enumerate(uniq)}
+        codes = np.fromiter((lut[v] if not m else 0 for v, m in zip(ser.tolist(), isnull)),
+                            dtype=np.int32, count=len(ser))
+        col = cls.from_numpy(codes, isnull, device)
+        col.dictionary = uniq
+        return col
+
+    @classmethod
+    def from_pandas(cls, ser: pd.Series, device=None) -> "Column":
+        device = device or default_device()
+        dt = ser.dtype
+        if isinstance(dt, pd.CategoricalDtype):
+            ser = ser.astype(object)
+            dt = ser.dtype
+        if pd.api.types.is_bool_dtype(dt) and not pd.api.types.is_extension_array_dtype(dt):
+            return cls.from_numpy(ser.to_numpy(), None, device)
+        if pd.api.types.is_extension_array_dtype(dt) and (
+                pd.api.types.is_integer_dtype(dt) or pd.api.types.is_float_dtype(dt)
+                or pd.api.types.is_bool_dtype(dt)):
+            mask = ser.isna().to_numpy()
+            base = np.dtype(str(dt).lower().replace("boolean", "bool"))
+            vals = ser.fillna(0).to_numpy(dtype=base)
+            return cls.from_numpy(vals, mask, device)
+        if pd.api.types.is_numeric_dtype(dt):
+            arr = ser.to_numpy()
+            mask = np.isnan(arr) if np.issubdtype(arr.dtype, np.floating) else None
+            return cls.from_numpy(arr, mask, device)
+        # object / string: strings or lists
+        vals = ser.tolist()
+        first = next((v for v in vals if v is not None and not (isinstance(v, float) and np.isnan(v))), None)
+        if isinstance(first, (list, tuple, np.ndarray)):
+            return cls.from_lists(vals, device)
+        return cls.from_strings(vals, device)
+
+    @classmethod
+    def from_lists(cls, rows, device=None) -> "Column":
+        device = device or default_device()
+        lens = np.fromiter((0 if r is None else len(r) for r in rows), dtype=np.int64, count=len(rows))
+        offsets = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        flat: List = []
+        for r in rows:
+            if r is not None:
+                flat.extend(list(r))
+        leaf = cls.from_pandas(pd.Series(flat, dtype=object if (flat and isinstance(flat[0], str)) else None), device) \
+            if flat else cls(torch.zeros(0, dtype=torch.int64, device=device))
+        leaf.offsets = torch.from_numpy(offsets).to(device)
+        return leaf
+
+    # ------------------------------------------------------------- device -> host
+    def materialize_fill(self) -> "Column":
+        """Apply a deferred FillMissing on the host side of a conversion."""
+        return self
+
+    def to_numpy(self):
+        """(values ndarray, null-mask ndarray|None) of the leaf values."""
+        vals = self.data.detach().cpu().numpy()
+        if self.is_bool:
+            vals = vals.astype(bool)
+        mask = None
+        if self.validity is not None:
+            mask = ~unpack_validity(self.validity, self.data.numel()).cpu().numpy()
+            if not mask.any():
+                mask = None
+        return vals, mask
+
+    def to_pandas(self, name=None) -> pd.Series:
+        vals, mask = self.to_numpy()
+        if self.dictionary is not None:
+            out = np.empty(len(vals), dtype=object)
+            if len(vals):
+                out[:] = self.dictionary[np.clip(vals, 0, max(len(self.dictionary) - 1, 0))] \
+                    if len(self.dictionary) else None
+            if mask is not None:
+                out[mask] = None
+            leaf = out
+        elif mask is not None:
+            # pandas' own convention: numeric column with nulls -> float64 NaN
+            leaf = vals.astype("float64") if not np.issubdtype(vals.dtype, np.floating) else vals.copy()
+            leaf[mask] = np.nan
+        else:
+            leaf = vals
+        if self.offsets is not None:
+            off = self.offsets.cpu().numpy()
+            rows = [leaf[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+            return pd.Series(rows, name=name, dtype=object)
+        return pd.Series(leaf, name=name)
+
+
+class DeviceFrame:
+    """An ordered set of equal-length Columns — the engine's DataFrame."""
+
+    def __init__(self, columns: Optional[Dict[str, Column]] = None):
+        self._cols: Dict[str, Column] = dict(columns or {})
+
+    @classmethod
+    def from_pandas(cls, df: pd.DataFrame, device=None, columns=None) -> "DeviceFrame":
+        names = list(columns) if columns is not None else list(df.columns)
+        return cls({n: Column.from_pandas(df[n], device) for n in names})
+
+    @classmethod
+    def from_dict(cls, d, device=None) -> "DeviceFrame":
+        out = {}
+        for k, v in d.items():
+            if isinstance(v, Column):
+                out[k] = v
+            elif isinstance(v, torch.Tensor):
+                out[k] = Column(v)
+            elif isinstance(v, tuple) and len(v) == 2 and isinstance(v[0], torch.Tensor):
+                out[k] = Column(v[0], v[1])
+            else:
+                out[k] = Column.from_pandas(pd.Series(v), device)
+        return cls(out)
+
+    @property
+    def columns(self) -> List[str]:
+        return list(self._cols)
+
+    def __contains__(self, name):
+        return name in self._cols
+
+    def __getitem__(self, name) -> Column:
+        if isinstance(name, (list, tuple)):
+            return DeviceFrame({n: self._cols[n] for n in name})
+        return self._cols[name]
+
+    def __setitem__(self, name, col: Column):
+        self._cols[name] = col
+
+    def __len__(self):
+        for c in self._cols.values():
+            return c.nrows
+        return 0
+
+    def copy(self) -> "DeviceFrame":
+        return DeviceFrame(dict(self._cols))
+
+    def drop(self, names) -> "DeviceFrame":
+        return DeviceFrame({k: v for k, v in self._cols.items() if k not in set(names)})
+
+    def items(self):
+        return self._cols.items()
+
+    def to_pandas(self) -> pd.DataFrame:
+        from .ops.fill import materialize  # deferred fills are applied by the fill kernel
+        out = {}
+        for k, c in self._cols.items():
+            out[k] = materialize(c).to_pandas(k)
+        return pd.DataFrame(out) if out else pd.DataFrame()
