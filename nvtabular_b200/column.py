@@ -139,6 +139,8 @@ class Column:
                 arr = arr.astype("float32" if arr.dtype.itemsize < 4 else "float64")
             else:
                 raise TypeError(f"unsupported column dtype {arr.dtype}")
+        if not arr.flags.writeable:
+            arr = arr.copy()
         t = torch.from_numpy(arr).to(device)
         validity = None
         if mask is not None and mask.any():

@@ -1,0 +1,377 @@
+"""Thin, typed Python face of the C-ABI (include/nvtb200.h): every function
+here is one or two calls into libnvtb200.so on Column buffers.  The operator
+classes in nvtabular_b200/ops are written against this module only.
+
+No arithmetic happens in Python on row data; torch is used to allocate output
+buffers and to read back O(#columns) scalars.
+"""
+import ctypes
+from ctypes import byref, c_int, c_int64, c_void_p
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .column import Column
+
+_CODE2TORCH = {_lib.I32: torch.int32, _lib.I64: torch.int64, _lib.F32: torch.float32,
+               _lib.F64: torch.float64, _lib.U8: torch.uint8}
+_NP2CODE = {np.dtype("int32"): _lib.I32, np.dtype("int64"): _lib.I64,
+            np.dtype("float32"): _lib.F32, np.dtype("float64"): _lib.F64,
+            np.dtype("uint8"): _lib.U8, np.dtype("bool"): _lib.U8}
+NAN = float("nan")
+kernel_launches = 0  # counted for bench.py's "gpu_launches"
+
+
+def _count(n=1):
+    global kernel_launches
+    kernel_launches += n
+
+
+def dtype_code(dt) -> int:
+    if isinstance(dt, torch.dtype):
+        return {v: k for k, v in _CODE2TORCH.items()}[dt]
+    return _NP2CODE[np.dtype(dt)]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return c_void_p(t.data_ptr()) if t is not None and t.numel() else None
+
+
+def _fills(cols: Sequence[Column]):
+    return _lib.double_array([NAN if c.fill is None else float(c.fill) for c in cols])
+
+
+def _descs(cols: Sequence[Column]):
+    return _lib.col_array([c.desc() for c in cols])
+
+
+def _check_same_len(cols: Sequence[Column]) -> int:
+    n = cols[0].data.numel()
+    for c in cols:
+        if c.data.numel() != n:
+            raise ValueError("columns of one call must have the same length")
+    return n
+
+
+# ----------------------------------------------------------------- moments
+class Moments:
+    """Running {count, sum, sumsq, min, max} per column on the device
+    (nvtb_moments_*; replaces nvtabular/ops/moments.py:28-116)."""
+
+    def __init__(self, ncols: int, device=None):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.ncols = ncols
+        self.acc = torch.empty(ncols * 5, dtype=torch.float64, device=device or "cuda")
+        _lib.check(self.lib.nvtb_moments_init(_ptr(self.acc), ncols, _lib.stream_ptr()))
+        _count()
+
+    def accumulate(self, cols: Sequence[Column]):
+        assert len(cols) == self.ncols
+        n = _check_same_len(cols)
+        _lib.check(self.lib.nvtb_moments_accumulate(
+            _descs(cols), self.ncols, n, _fills(cols), _ptr(self.acc), _lib.stream_ptr()))
+        _count(2)
+
+    def allreduce(self):
+        """Cross-GPU merge: one NCCL all-reduce of 3 sums + min + max per column
+        (replaces the dask tree of moments.py:45-55)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        a = self.acc.view(self.ncols, 5)
+        sums = a[:, 0:3].contiguous()
+        mn = a[:, 3].contiguous()
+        mx = a[:, 4].contiguous()
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        a[:, 0:3] = sums
+        a[:, 3] = mn
+        a[:, 4] = mx
+
+    def result(self):
+        """-> dict of numpy arrays: count,sum,sumsq,min,max,mean,var,std."""
+        acc = self.acc.cpu().numpy().astype(np.float64)
+        out = np.zeros(self.ncols * 3, dtype=np.float64)
+        _lib.check(self.lib.nvtb_moments_finalize(
+            acc.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), self.ncols,
+            out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        a = acc.reshape(self.ncols, 5)
+        o = out.reshape(self.ncols, 3)
+        return {"count": a[:, 0], "sum": a[:, 1], "sumsq": a[:, 2], "min": a[:, 3], "max": a[:, 4],
+                "mean": o[:, 0], "var": o[:, 1], "std": o[:, 2]}
+
+
+# ------------------------------------------------------------- transforms
+def _alloc_like(cols: Sequence[Column], dtype: torch.dtype) -> List[torch.Tensor]:
+    return [torch.empty(c.data.numel(), dtype=dtype, device=c.data.device) for c in cols]
+
+
+def fill_apply(cols: Sequence[Column], fill_vals: Sequence[float], add_binary_cols=False):
+    """FillMissing (nvtb_fill_apply).  Returns (filled columns, indicator columns|None)."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    n = _check_same_len(cols)
+    outs = [torch.empty_like(c.data) for c in cols]
+    flags = [torch.empty(n, dtype=torch.uint8, device=c.data.device) for c in cols] if add_binary_cols else None
+    _lib.check(lib.nvtb_fill_apply(
+        _descs(cols), len(cols), n, _lib.double_array(fill_vals),
+        _lib.ptr_array([o.data_ptr() for o in outs]),
+        _lib.ptr_array([f.data_ptr() for f in flags]) if flags else None, _lib.stream_ptr()))
+    _count()
+    out_cols = [Column(o, None, c.offsets, None, None, c.is_bool) for o, c in zip(outs, cols)]
+    flag_cols = [Column(f, None, c.offsets, is_bool=True) for f, c in zip(flags, cols)] if flags else None
+    return out_cols, flag_cols
+
+
+def normalize_apply(cols: Sequence[Column], means, stds, out_dtype=np.float64):
+    _lib.require_cuda()
+    lib = _lib.load()
+    n = _check_same_len(cols)
+    code = dtype_code(out_dtype)
+    outs = _alloc_like(cols, _CODE2TORCH[code])
+    _lib.check(lib.nvtb_normalize_apply(
+        _descs(cols), len(cols), n, _fills(cols), _lib.double_array(means), _lib.double_array(stds),
+        _lib.ptr_array([o.data_ptr() for o in outs]), code, _lib.stream_ptr()))
+    _count()
+    return [Column(o, None if c.fill is not None else c.validity, c.offsets) for o, c in zip(outs, cols)]
+
+
+def minmax_apply(cols: Sequence[Column], mins, maxs, out_dtype=np.float64):
+    _lib.require_cuda()
+    lib = _lib.load()
+    n = _check_same_len(cols)
+    code = dtype_code(out_dtype)
+    outs = _alloc_like(cols, _CODE2TORCH[code])
+    _lib.check(lib.nvtb_minmax_apply(
+        _descs(cols), len(cols), n, _fills(cols), _lib.double_array(mins), _lib.double_array(maxs),
+        _lib.ptr_array([o.data_ptr() for o in outs]), code, _lib.stream_ptr()))
+    _count()
+    return [Column(o, None if c.fill is not None else c.validity, c.offsets) for o, c in zip(outs, cols)]
+
+
+def hash_bucket(cols: Sequence[Column], num_buckets: int, add: int = 0, out_dtype=np.int32) -> torch.Tensor:
+    """hash(cols...) % num_buckets + add (nvtb_hash_bucket_apply)."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    n = _check_same_len(cols)
+    code = dtype_code(out_dtype)
+    out = torch.empty(n, dtype=_CODE2TORCH[code], device=cols[0].data.device)
+    _lib.check(lib.nvtb_hash_bucket_apply(_descs(cols), len(cols), n, int(num_buckets), int(add),
+                                          _ptr(out), code, _lib.stream_ptr()))
+    _count()
+    return out
+
+
+def hash_values(col: Column) -> torch.Tensor:
+    """raw uint64 value hashes as an int64 tensor (bit pattern)."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    n = col.data.numel()
+    out = torch.empty(n, dtype=torch.int64, device=col.data.device)
+    _lib.check(lib.nvtb_hash_values(_descs([col]), n, _ptr(out), _lib.stream_ptr()))
+    _count()
+    return out
+
+
+def pack_keys2(a: Column, b: Column) -> Column:
+    """(a, b) int32 pair -> one order-preserving int64 key column."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    n = _check_same_len([a, b])
+    keys = torch.empty(n, dtype=torch.int64, device=a.data.device)
+    need_mask = a.validity is not None and b.validity is not None
+    nbytes = (((n + 7) // 8 + 31) // 32) * 32
+    mask = torch.zeros(nbytes, dtype=torch.uint8, device=a.data.device) if need_mask else None
+    _lib.check(lib.nvtb_pack_keys2(_descs([a]), _descs([b]), n, _ptr(keys), _ptr(mask), _lib.stream_ptr()))
+    _count()
+    return Column(keys, mask)
+
+
+def unpack_keys2(keys: np.ndarray):
+    """host inverse of pack_keys2: int64 -> (a int32, b int32); INT32_MIN marks a null component."""
+    k = keys.astype(np.int64)
+    a = (k >> 32).astype(np.int32)
+    b = ((k & 0xFFFFFFFF).astype(np.uint32) ^ np.uint32(0x80000000)).astype(np.uint32).view(np.int32)
+    return a, b
+
+
+# ------------------------------------------------------------- hash aggregation
+class HashAgg:
+    """groupby(key, dropna=False) -> size [, sum/sumsq/min/max per cont col]
+    (nvtb_hashagg_*; replaces nvtabular/ops/categorify.py:955-1137)."""
+
+    def __init__(self, n_agg: int = 0, capacity_hint: int = 0):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.n_agg = n_agg
+        self.h = c_void_p()
+        _lib.check(self.lib.nvtb_hashagg_create(byref(self.h), n_agg, int(capacity_hint)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) is not None and self.h.value:
+                self.lib.nvtb_hashagg_destroy(self.h)
+                self.h = c_void_p()
+        except Exception:
+            pass
+
+    def insert(self, key: Column, agg_cols: Sequence[Column] = ()):
+        n = key.data.numel()
+        assert len(agg_cols) == self.n_agg
+        for c in agg_cols:
+            assert c.data.numel() == n
+        _lib.check(self.lib.nvtb_hashagg_insert(
+            self.h, _descs([key]), _descs(agg_cols) if self.n_agg else None, n, _lib.stream_ptr()))
+        _count(max(1, (n + (1 << 23) - 1) >> 23))
+
+    def merge(self, keys: torch.Tensor, sizes: torch.Tensor, vals: Optional[torch.Tensor] = None):
+        n = keys.numel()
+        _lib.check(self.lib.nvtb_hashagg_merge(self.h, _ptr(keys), _ptr(sizes), _ptr(vals), n, _lib.stream_ptr()))
+        _count(max(1, (n + (1 << 23) - 1) >> 23) if n else 0)
+
+    def add_null_group(self, size: int, vals: Optional[np.ndarray] = None):
+        arr = _lib.double_array(list(vals)) if vals is not None and self.n_agg else None
+        _lib.check(self.lib.nvtb_hashagg_add_null_group(self.h, int(size), arr))
+
+    def size(self):
+        nu, ns = c_int64(0), c_int64(0)
+        _lib.check(self.lib.nvtb_hashagg_size(self.h, byref(nu), byref(ns), _lib.stream_ptr()))
+        return nu.value, ns.value
+
+    def export(self, device="cuda"):
+        """-> (keys int64[U], sizes int64[U], vals float64[U, n_agg, 4] | None,
+                null_size, null_vals ndarray[n_agg,4] | None), unordered."""
+        nu, ns = self.size()
+        keys = torch.empty(nu, dtype=torch.int64, device=device)
+        sizes = torch.empty(nu, dtype=torch.int64, device=device)
+        vals = torch.empty((nu, self.n_agg, 4), dtype=torch.float64, device=device) if self.n_agg else None
+        null_vals = (ctypes.c_double * (4 * max(self.n_agg, 1)))()
+        _lib.check(self.lib.nvtb_hashagg_export(self.h, _ptr(keys), _ptr(sizes), _ptr(vals),
+                                                null_vals if self.n_agg else None, _lib.stream_ptr()))
+        _count()
+        nv = np.array(list(null_vals), dtype=np.float64).reshape(-1, 4)[: self.n_agg] if self.n_agg else None
+        return keys, sizes, vals, ns, nv
+
+
+def partition_by_owner(keys: torch.Tensor, n_parts: int):
+    """-> (perm int64[n], counts list[int]) grouping rows by hash-owner."""
+    lib = _lib.load()
+    n = keys.numel()
+    perm = torch.empty(n, dtype=torch.int64, device=keys.device)
+    counts = (c_int64 * n_parts)()
+    _lib.check(lib.nvtb_partition_by_owner(_ptr(keys), n, n_parts, _ptr(perm), counts, _lib.stream_ptr()))
+    _count(2)
+    return perm, [int(c) for c in counts]
+
+
+def gather_i64(src: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(perm.numel(), dtype=torch.int64, device=src.device)
+    _lib.check(lib.nvtb_gather_i64(_ptr(src), _ptr(perm), perm.numel(), _ptr(out), _lib.stream_ptr()))
+    _count()
+    return out
+
+
+def gather_f64_rows(src: torch.Tensor, perm: torch.Tensor, width: int) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty((perm.numel(), width), dtype=torch.float64, device=src.device)
+    _lib.check(lib.nvtb_gather_f64_rows(_ptr(src), _ptr(perm), perm.numel(), width, _ptr(out), _lib.stream_ptr()))
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------ vocabulary
+class Vocab:
+    """Ordered vocabulary + device lookup (nvtb_vocab_*; replaces
+    _write_uniques/_save_encodings/_encode, categorify.py:1149-1337,719-822,1558-1807)."""
+
+    def __init__(self, handle, lib):
+        self.h = handle
+        self.lib = lib
+        info = _lib.nvtb_vocab_info_t()
+        _lib.check(lib.nvtb_vocab_info(self.h, byref(info)))
+        self.n_kept, self.n_total = info.n_kept, info.n_total
+        self.null_size, self.oov_size, self.unique_size = info.null_size, info.oov_size, info.unique_size
+
+    @classmethod
+    def build(cls, keys: torch.Tensor, sizes: torch.Tensor, null_size=0, freq_threshold=0,
+              max_size=0, num_buckets=0):
+        _lib.require_cuda()
+        lib = _lib.load()
+        h = c_void_p()
+        _lib.check(lib.nvtb_vocab_build(byref(h), _ptr(keys), _ptr(sizes), keys.numel(), int(null_size),
+                                        int(freq_threshold or 0), int(max_size or 0), int(num_buckets or 0),
+                                        _lib.stream_ptr()))
+        _count(8)
+        return cls(h, lib)
+
+    @classmethod
+    def from_arrays(cls, keys: torch.Tensor, sizes: Optional[torch.Tensor] = None):
+        _lib.require_cuda()
+        lib = _lib.load()
+        h = c_void_p()
+        _lib.check(lib.nvtb_vocab_from_arrays(byref(h), _ptr(keys), _ptr(sizes), keys.numel(), _lib.stream_ptr()))
+        _count(2)
+        return cls(h, lib)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) is not None and self.h.value:
+                self.lib.nvtb_vocab_destroy(self.h)
+                self.h = c_void_p()
+        except Exception:
+            pass
+
+    def export(self, device="cuda", with_sizes=True):
+        keys = torch.empty(self.n_kept, dtype=torch.int64, device=device)
+        sizes = torch.empty(self.n_kept, dtype=torch.int64, device=device) if with_sizes else None
+        _lib.check(self.lib.nvtb_vocab_export(self.h, _ptr(keys), _ptr(sizes), _lib.stream_ptr()))
+        return keys, sizes
+
+    def encode(self, key: Column, null_label=1, oov_label=2, first_label=3, num_buckets=0,
+               hash_cols: Sequence[Column] = (), out_dtype=np.int64) -> torch.Tensor:
+        n = key.data.numel()
+        code = dtype_code(out_dtype)
+        out = torch.empty(n, dtype=_CODE2TORCH[code], device=key.data.device)
+        _lib.check(self.lib.nvtb_encode_apply(
+            self.h, _descs([key]), n, int(null_label), int(oov_label), int(first_label),
+            int(num_buckets or 0), _descs(hash_cols) if hash_cols else None, len(hash_cols),
+            _ptr(out), code, _lib.stream_ptr()))
+        _count()
+        return out
+
+
+class GroupStats:
+    """key -> row of a stats matrix, gathered per row (nvtb_groupstats_*)."""
+
+    def __init__(self, keys: torch.Tensor, stats: torch.Tensor, null_row: int = -1):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.h = c_void_p()
+        stats = stats.contiguous().to(torch.float64)
+        self.width = int(stats.shape[1])
+        _lib.check(self.lib.nvtb_groupstats_create(byref(self.h), _ptr(keys), keys.numel(), _ptr(stats),
+                                                   self.width, int(null_row), _lib.stream_ptr()))
+        _count(2)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) is not None and self.h.value:
+                self.lib.nvtb_groupstats_destroy(self.h)
+                self.h = c_void_p()
+        except Exception:
+            pass
+
+    def gather(self, key: Column, cols: Sequence[int], miss_vals: Sequence[float], out_dtypes) -> List[torch.Tensor]:
+        n = key.data.numel()
+        codes = [dtype_code(d) for d in out_dtypes]
+        outs = [torch.empty(n, dtype=_CODE2TORCH[c], device=key.data.device) for c in codes]
+        _lib.check(self.lib.nvtb_groupstats_gather(
+            self.h, _descs([key]), n, _lib.int_array(cols), len(cols), _lib.double_array(miss_vals),
+            _lib.ptr_array([o.data_ptr() for o in outs]), _lib.int_array(codes), _lib.stream_ptr()))
+        _count()
+        return outs

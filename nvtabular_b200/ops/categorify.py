@@ -1,0 +1,530 @@
+"""Categorify (reference nvtabular/ops/categorify.py:58-613, helpers to :1897).
+
+Same constructor, label space, artefacts and error behaviour as the reference;
+everything underneath is different:
+
+  fit        per partition, every column group is folded into a resident
+             device hash table (K3, engine.HashAgg) — no per-partition
+             groupby frames, no tree of concat+groupby, no host spill;
+             across GPUs the partial tables are exchanged by key-hash owner
+             (all-to-all), merged, all-gathered, and every rank builds the
+             identical vocabulary (K4: (size desc, key asc) ordering,
+             freq_threshold / max_size cut) and lookup table (K5).
+  transform  one in-order probe pass per column (K5) — no merge, no sort back.
+"""
+import os
+import warnings
+from copy import deepcopy
+from typing import Dict, List, Optional
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .. import engine
+from ..column import Column, DeviceFrame
+from ..graph import ColumnSelector, Tags
+from .base import StatOperator
+from .hash_bucket import emb_sz_rule
+from .keyspace import ComboKeySpace, KeySpace, _leaf
+
+PAD_OFFSET, NULL_OFFSET, OOV_OFFSET = 0, 1, 2   # categorify.py:51-55
+EAGER_ARTIFACT_ROWS = 1 << 20                   # larger vocabularies are written lazily
+
+
+def _make_name(*args, sep="_"):
+    return sep.join(args)
+
+
+def _resolve(opt, name, default=None):
+    if isinstance(opt, dict):
+        return opt.get(name, default)
+    return opt if opt is not None else default
+
+
+class FittedVocab:
+    """What the reference keeps as `unique.<name>.parquet` + `meta.<name>.parquet`
+    (categorify.py:719-822): device lookup handle + host metadata; the parquet
+    files are (re)written from it."""
+
+    def __init__(self, name, key_names, space, vocab: engine.Vocab, num_buckets=None,
+                 has_sizes=True, index_start=None):
+        self.name = name
+        self.key_names = list(key_names)      # column names inside the parquet file
+        self.space = space                    # KeySpace | ComboKeySpace
+        self.vocab = vocab
+        self.num_buckets = num_buckets
+        self.has_sizes = has_sizes
+        oov_count = num_buckets or 1
+        self.index_start = OOV_OFFSET + oov_count if index_start is None else index_start
+        self.path = None
+        self._written = False
+
+    @property
+    def n_kept(self):
+        return self.vocab.n_kept
+
+    def unique_frame(self) -> pd.DataFrame:
+        keys, sizes = self.vocab.export(with_sizes=self.has_sizes)
+        k = keys.cpu().numpy()
+        if isinstance(self.space, ComboKeySpace):
+            comps = self.space.decode(k)
+            data = {n: pd.Series(v, dtype=object) for n, v in zip(self.key_names, comps)}
+        else:
+            data = {self.key_names[0]: self.space.decode(k)}
+        df = pd.DataFrame(data)
+        if self.has_sizes:
+            df[f"{self.name}_size"] = sizes.cpu().numpy()
+        df.index = pd.RangeIndex(self.index_start, self.index_start + len(df))
+        return df
+
+    def meta_frame(self) -> pd.DataFrame:
+        oov_count = self.num_buckets or 1
+        meta = {
+            "kind": ["pad", "null", "oov", "unique"],
+            "offset": [PAD_OFFSET, NULL_OFFSET, OOV_OFFSET, OOV_OFFSET + oov_count],
+            "num_indices": [1, 1, oov_count, self.vocab.n_kept],
+        }
+        if self.has_sizes:
+            meta["num_observed"] = [0, self.vocab.null_size, self.vocab.oov_size, self.vocab.unique_size]
+        return pd.DataFrame(meta)
+
+    def write(self, base_path, force=False):
+        """categorify.py:731-822: unique.<name>.parquet (index = label) + meta.<name>.parquet."""
+        os.makedirs(base_path, exist_ok=True)
+        self.path = "/".join([str(base_path), f"unique.{self.name}.parquet"])
+        meta_path = "/".join([str(base_path), f"meta.{self.name}.parquet"])
+        self.meta_frame().to_parquet(meta_path)
+        if force or self.vocab.n_kept <= EAGER_ARTIFACT_ROWS:
+            df = self.unique_frame()
+            if len(df) == 0:   # categorify.py:1318-1324: a single null row
+                df = pd.DataFrame({n: pd.Series([None], dtype=object) for n in self.key_names})
+            df.to_parquet(self.path, compression=None)
+            self._written = True
+        return self.path
+
+    def ensure_written(self):
+        if self.path is not None and not self._written:
+            self.write(os.path.dirname(self.path), force=True)
+
+
+class _Categories(dict):
+    """storage name -> parquet path, like the reference's `Categorify.categories`.
+    Reading a path makes sure a lazily written (very large) vocabulary file exists."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.fitted: Dict[str, FittedVocab] = {}
+
+    def __getitem__(self, key):
+        fv = self.fitted.get(key)
+        if fv is not None:
+            fv.ensure_written()
+        return super().__getitem__(key)
+
+
+class Categorify(StatOperator):
+    def __init__(self, freq_threshold=0, out_path=None, cat_cache="host", dtype=None, on_host=True,
+                 encode_type="joint", name_sep="_", search_sorted=False, num_buckets=None, vocabs=None,
+                 max_size=0, single_table=False, cardinality_memory_limit=None, tree_width=None,
+                 split_out=1, split_every=8, **kwargs):
+        # categorify.py:226-241
+        if "start_index" in kwargs:
+            raise ValueError(
+                "start_index is now deprecated. `Categorify` will always reserve index `0` for "
+                "user-specific purposes, and will use index `1` for null values.")
+        if "na_sentinel" in kwargs:
+            raise ValueError(
+                "na_sentinel is now deprecated. `Categorify` will always reserve index `1` for null "
+                "values, and the following `num_buckets` indices for out-of-vocabulary values "
+                "(or just index `2` if `num_buckets is None`).")
+        if kwargs:
+            raise ValueError(f"Unrecognized key-word arguments: {kwargs}")
+        if num_buckets and not (max_size or freq_threshold):   # :246-251
+            warnings.warn(
+                "You are setting num_buckets without using max_size or freq_threshold to restrict "
+                "the number of distinct categories. Are you sure this is what you want?")
+        self.name_sep = name_sep
+        self.storage_name = {}
+        if encode_type not in ("joint", "combo"):               # :287-290
+            raise ValueError(f"encode_type={encode_type} not supported.")
+        if encode_type == "combo" and vocabs is not None:
+            raise ValueError("Passing in vocabs is not supported with a combo encoding.")
+        super().__init__()
+        self.single_table = single_table
+        self.freq_threshold = freq_threshold or 0
+        self.out_path = out_path or "./"
+        self.dtype = dtype
+        self.on_host = on_host            # accepted, meaningless here: nothing spills to host
+        self.cat_cache = cat_cache        # accepted: the lookup table always lives in HBM
+        self.encode_type = encode_type
+        self.search_sorted = search_sorted
+        self.cardinality_memory_limit = cardinality_memory_limit
+        self.split_every = split_every    # accepted: there is no reduction tree
+        self.split_out = split_out        # accepted: sharding is by key-hash owner across GPUs
+        if tree_width is not None:        # :1900-1907
+            warnings.warn("The tree_width argument is now deprecated, and will be ignored. "
+                          "Please use split_out and split_every.", FutureWarning)
+        if self.search_sorted and self.freq_threshold:           # :307-310
+            raise ValueError("cannot use search_sorted=True with anything else than the default freq_threshold")
+        if num_buckets == 0:                                     # :311-322
+            raise ValueError("For hashing num_buckets should be an int > 1, otherwise set num_buckets=None.")
+        elif isinstance(num_buckets, dict) or isinstance(num_buckets, int) or num_buckets is None:
+            self.num_buckets = num_buckets
+        else:
+            raise ValueError(f"`num_buckets` must be dict or int, got type {type(num_buckets)}")
+        if isinstance(max_size, dict) or isinstance(max_size, int) or max_size is None:
+            self.max_size = max_size
+        else:
+            raise ValueError(f"max_size must be dict or int, got type {type(max_size)}")
+        if freq_threshold and max_size:                          # :329-330
+            raise ValueError("cannot use freq_threshold param together with max_size param")
+        if self.num_buckets is not None:                         # :332-338
+            warnings.warn("Performing a hash-based transformation. Do not expect Categorify to be "
+                          "consistent on GPU and CPU with this num_buckets setting!")
+        self._user_vocabs = vocabs
+        self.vocabs = {}
+        self.categories = _Categories()
+        if vocabs is not None:
+            self._check_vocabs(vocabs)
+
+    # ------------------------------------------------------------------ vocabs=
+    def _check_vocabs(self, vocabs):
+        ok_series = isinstance(vocabs, dict) and all(isinstance(v, pd.Series) for v in vocabs.values())
+        ok_paths = isinstance(vocabs, dict) and all(isinstance(v, str) for v in vocabs.values())
+        if not (ok_series or ok_paths):
+            raise ValueError("Unrecognized vocab type, please provide either a dictionary with paths "
+                             "to parquet files or a dictionary with pandas Series objects.")
+
+    def _nb(self, name):
+        nb = _resolve(self.num_buckets, name)
+        return nb or None
+
+    def _vocab_from_values(self, col_name, values: pd.Series, sizes=None, index_start=None) -> FittedVocab:
+        """process_vocabs (categorify.py:421-454): labels are 2 + B + position after dropna()."""
+        values = values.dropna().reset_index(drop=True)
+        if values.dtype == object or str(values.dtype) in ("str", "string"):
+            space = KeySpace("str", np.array(sorted(set(values.tolist())), dtype=object))
+        elif np.issubdtype(values.dtype, np.floating):
+            space = KeySpace("float", None, values.dtype)
+        else:
+            space = KeySpace("int", None, np.dtype("int64") if values.dtype.itemsize == 8 else np.dtype("int32"))
+        keys = torch.from_numpy(space.encode_values(values).astype(np.int64)).cuda()
+        szt = torch.from_numpy(np.asarray(sizes, dtype=np.int64)).cuda() if sizes is not None else None
+        vocab = engine.Vocab.from_arrays(keys, szt)
+        return FittedVocab(col_name, [col_name], space, vocab, self._nb(col_name),
+                           has_sizes=sizes is not None, index_start=index_start)
+
+    def _load_user_vocabs(self):
+        if not self._user_vocabs or self.vocabs:
+            return
+        base = os.path.join(self.out_path, "categories")
+        for col, v in self._user_vocabs.items():
+            name = _make_name(*col, sep=self.name_sep) if isinstance(col, tuple) else col
+            if isinstance(v, str):
+                fv = self._vocab_from_parquet(name, v)
+                fv.path, fv._written = v, True
+            else:
+                fv = self._vocab_from_values(name, v)
+                fv.write(base, force=True)
+            self.vocabs[name] = fv
+        for name, fv in self.vocabs.items():
+            self.categories[name] = fv.path
+            self.categories.fitted[name] = fv
+
+    def _vocab_from_parquet(self, name, path) -> FittedVocab:
+        df = pd.read_parquet(path)
+        size_col = f"{name}_size"
+        key_cols = [c for c in df.columns if c != size_col]
+        sizes = df[size_col] if size_col in df.columns else None
+        keep = ~df[key_cols[0]].isna()
+        start = int(df.index[0]) if len(df) and isinstance(df.index, pd.RangeIndex) else None
+        return self._vocab_from_values(name, df[key_cols[0]][keep], sizes[keep] if sizes is not None else None,
+                                       index_start=start)
+
+    # ----------------------------------------------------------------------- fit
+    def _groups(self, col_selector: ColumnSelector):
+        """[(storage name, [column names])] for every column group to fit."""
+        out = []
+        for g in col_selector.grouped_names:
+            names = list(g) if isinstance(g, tuple) else [g]
+            out.append((_make_name(*names, sep=self.name_sep), names))
+        return out
+
+    def fit(self, col_selector: ColumnSelector, ddf):
+        # categorify.py:350-357
+        columns_all = col_selector.names
+        if len(columns_all) != len(set(columns_all)) and self.encode_type == "joint":
+            raise ValueError("Same column name included in multiple groups.")
+        for group in col_selector.subgroups:
+            if len(group.names) > 1:
+                name = _make_name(*group.names, sep=self.name_sep)
+                for col in group.names:
+                    self.storage_name[col] = name
+        self._load_user_vocabs()
+        groups = [(s, n) for s, n in self._groups(col_selector) if s not in self.vocabs]
+        if not groups:
+            return {}
+        parts = list(ddf)   # device-resident partitions (post upstream transforms)
+        fitted = {}
+        for storage, names in groups:
+            fitted[storage] = self._fit_group(storage, names, parts)
+        return fitted
+
+    def _fit_group(self, storage, names, parts) -> FittedVocab:
+        combo = self.encode_type == "combo" and len(names) > 1
+        if combo:
+            comp_parts = [[_leaf(df[n]) for n in names] for df in parts]
+            if any(c.is_list for df in parts for c in (df[n] for n in names)):
+                raise ValueError("Can't categorical encode multiple list columns")
+            space = ComboKeySpace.fit(comp_parts) if parts else ComboKeySpace([KeySpace("int")] * len(names))
+            key_names = names
+        else:
+            cols_all = [df[n] for df in parts for n in names]
+            space = KeySpace.for_columns([_leaf(c) for c in cols_all]) if cols_all else KeySpace("int", None, np.dtype("int64"))
+            key_names = [storage]
+        agg = engine.HashAgg(0)
+        for df in parts:
+            if combo:
+                agg.insert(space.keys_for([df[n] for n in names]))
+            else:
+                for n in names:          # joint encoding: every column feeds the SAME table
+                    agg.insert(space.keys_for(df[n]))
+        keys, sizes, null_size = _global_unique_merge(agg)
+        ft = _resolve(self.freq_threshold, storage, 0) or 0
+        ms = _resolve(self.max_size, storage, 0) or 0
+        nb = self._nb(storage)
+        try:
+            vocab = engine.Vocab.build(keys, sizes, null_size, ft, ms, nb or 0)
+        except Exception as e:
+            if "max_size" in str(e):     # categorify.py:1206-1211
+                raise ValueError(
+                    "`max_size` can never be less than the maximum of `num_buckets + 2` and `3`, because "
+                    "we must always reserve pad, null and at least 1 oov-bucket index.") from e
+            raise
+        limit = self.cardinality_memory_limit
+        if limit:
+            limit = _parse_bytes(limit)
+            nbytes = vocab.n_total * 16
+            if nbytes > limit:           # categorify.py:1285-1294
+                warnings.warn(f"Category DataFrame (with columns: {key_names}) is {nbytes} bytes in size. "
+                              f"This is large compared to the suggested upper limit of {limit} bytes!"
+                              f"(12.5% of the total memory by default)")
+        return FittedVocab(storage, key_names, space, vocab, nb)
+
+    def fit_finalize(self, categories):
+        base = os.path.join(self.out_path, "categories")
+        idx_count = 0
+        merged = dict(self.vocabs)
+        merged.update(categories)
+        for name, fv in merged.items():
+            if self.single_table:                      # categorify.py:410-415, 1884-1897
+                fv.index_start = fv.index_start + idx_count
+                idx_count += max(fv.n_kept, 1) if fv.n_kept == 0 else fv.n_kept
+                fv._written = False
+            if name in categories or self.single_table:
+                fv.write(base)
+            self.categories[name] = fv.path
+            self.categories.fitted[name] = fv
+
+    def clear(self):
+        self.categories = _Categories()
+        for name, fv in self.vocabs.items():
+            self.categories[name] = fv.path
+            self.categories.fitted[name] = fv
+
+    def set_storage_path(self, new_path, copy=False):
+        for name, fv in self.categories.fitted.items():
+            if copy:
+                fv.write(os.path.join(new_path, "categories"), force=True)
+            else:
+                fv.path = fv.path.replace(str(self.out_path), str(new_path))
+            dict.__setitem__(self.categories, name, fv.path)
+        self.out_path = new_path
+
+    # ----------------------------------------------------------------- transform
+    def _fitted(self, storage) -> FittedVocab:
+        fv = self.categories.fitted.get(storage)
+        if fv is None:
+            path = dict.get(self.categories, storage)
+            if path is None:
+                raise KeyError(storage)
+            fv = self._vocab_from_parquet(storage, path)    # a workflow reloaded from disk
+            fv.path, fv._written = path, True
+            self.categories.fitted[storage] = fv
+        return fv
+
+    def transform(self, col_selector: ColumnSelector, df: DeviceFrame) -> DeviceFrame:
+        new_df = df.copy()
+        if isinstance(self.freq_threshold, dict):
+            assert all(x in self.freq_threshold for x in col_selector.names)
+        column_mapping = self.column_mapping(col_selector)
+        for name, use in column_mapping.items():
+            try:
+                use_name = use[0] if len(use) == 1 else list(use)
+                if use_name != name or self.encode_type == "joint":
+                    storage = self.storage_name.get(name, name)     # categorify.py:501-504
+                else:
+                    storage = name
+                new_df[name] = self._encode(name, use_name, storage, df)
+            except Exception as e:
+                raise RuntimeError(f"Failed to categorical encode column {name}") from e
+        return new_df
+
+    def _encode(self, name, use_name, storage, df) -> Column:
+        fv = self._fitted(storage)
+        # categorify.py:1607-1619: an int num_buckets is keyed by OUTPUT column name
+        buckets = self.num_buckets
+        if isinstance(buckets, int):
+            buckets = {n: buckets for n in self.column_mapping_names}
+        nb = buckets[storage] if buckets and storage in buckets else 0
+        num_oov = nb or 1
+        if self.single_table:                                       # :1683-1685
+            null_label = fv.index_start
+        else:
+            null_label = NULL_OFFSET
+        oov_label = null_label + 1
+        first_label = fv.index_start if self.single_table else oov_label + num_oov
+        if isinstance(use_name, list):
+            cols = [df[c] for c in use_name]
+            key = fv.space.keys_for(cols)
+            hash_cols = []
+            if nb:
+                for s, c in zip(fv.space.spaces, cols):
+                    hc = s.hash_column(c)
+                    hash_cols.append(hc if hc is not None else _leaf(c))
+            src = cols[0]
+            offsets = None
+        else:
+            src = df[use_name]
+            key = fv.space.keys_for(src)
+            hc = fv.space.hash_column(src) if nb else None
+            hash_cols = [hc] if hc is not None else ([_leaf(src)] if nb else [])
+            offsets = src.offsets
+        labels = fv.vocab.encode(key, null_label, oov_label, first_label, nb, hash_cols,
+                                 np.dtype(self.output_dtype))
+        return Column(labels, None, offsets)
+
+    @property
+    def column_mapping_names(self):
+        return self._mapping_names
+
+    def column_mapping(self, col_selector):
+        column_mapping = {}
+        if self.encode_type == "combo":                              # categorify.py:539-553
+            for group in col_selector.grouped_names:
+                if isinstance(group, (tuple, list)):
+                    name = _make_name(*group, sep=self.name_sep)
+                    group = [*group]
+                else:
+                    name = group
+                    group = [group]
+                column_mapping[name] = group
+        else:
+            column_mapping = super().column_mapping(col_selector)
+        self._mapping_names = list(column_mapping.keys())
+        return column_mapping
+
+    # -------------------------------------------------------------------- schema
+    def get_embedding_sizes(self, columns):
+        """_get_embeddings_dask (categorify.py:666-684)."""
+        buckets = self.num_buckets
+        if isinstance(buckets, int):
+            buckets = {name: buckets for name in columns}
+        out = {}
+        for col in columns:
+            num_rows = OOV_OFFSET
+            fv = self.categories.fitted.get(col)
+            if fv is not None:
+                num_rows += max(fv.n_kept, 1) if fv.n_kept == 0 else fv.n_kept
+            if isinstance(buckets, dict):
+                bucket_size = buckets.get(col, 0)
+            else:
+                bucket_size = 1
+            out[col] = emb_sz_rule(num_rows + bucket_size)
+        return out
+
+    def _compute_properties(self, col_schema, input_schema):
+        new_schema = super()._compute_properties(col_schema, input_schema)
+        col_name = col_schema.name
+        category_name = self.storage_name.get(col_name, col_name)
+        target_category_path = dict.get(self.categories, category_name, None)
+        cardinality, dimensions = self.get_embedding_sizes([category_name])[category_name]
+        to_add = {
+            "num_buckets": _resolve(self.num_buckets, col_name),
+            "freq_threshold": _resolve(self.freq_threshold, col_name),
+            "max_size": _resolve(self.max_size, col_name),
+            "cat_path": target_category_path,
+            "domain": {"min": 0, "max": cardinality - 1, "name": category_name},
+            "embedding_sizes": {"cardinality": cardinality, "dimension": dimensions},
+        }
+        return col_schema.with_properties({**new_schema.properties, **to_add})
+
+    @property
+    def output_tags(self):
+        return [Tags.CATEGORICAL]
+
+    @property
+    def output_dtype(self):
+        return self.dtype or np.int64
+
+
+def _parse_bytes(v):
+    if isinstance(v, (int, float)):
+        return int(v)
+    s = str(v).strip().upper()
+    units = {"KB": 10**3, "MB": 10**6, "GB": 10**9, "TB": 10**12, "KIB": 2**10, "MIB": 2**20,
+             "GIB": 2**30, "B": 1}
+    for u in sorted(units, key=len, reverse=True):
+        if s.endswith(u):
+            return int(float(s[: -len(u)]) * units[u])
+    return int(float(s))
+
+
+def _global_unique_merge(agg: engine.HashAgg):
+    """Local table -> globally merged (keys, sizes, null_size), identical on every rank.
+
+    Multi-GPU: (key, size) rows are routed to owner =
+    mix(key) % world with one all-to-all, each owner merges its shard (exact
+    global counts, disjoint keys), and the shards are all-gathered so every rank
+    can build the same vocabulary.  Replaces the dask tree reduce + filesystem
+    "broadcast" of categorify.py:1399-1540, 1627-1643."""
+    import torch.distributed as dist
+    keys, sizes, _, null_size, _ = agg.export()
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return keys, sizes, null_size
+    world = dist.get_world_size()
+    dev = keys.device
+    perm, counts = engine.partition_by_owner(keys, world)
+    send_k = engine.gather_i64(keys, perm)
+    send_s = engine.gather_i64(sizes, perm)
+    send_counts = torch.tensor(counts, dtype=torch.int64, device=dev)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts)
+    rc = [int(x) for x in recv_counts.cpu().tolist()]
+    recv_k = torch.empty(sum(rc), dtype=torch.int64, device=dev)
+    recv_s = torch.empty(sum(rc), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv_k, send_k, output_split_sizes=rc, input_split_sizes=counts)
+    dist.all_to_all_single(recv_s, send_s, output_split_sizes=rc, input_split_sizes=counts)
+    owner = engine.HashAgg(0, capacity_hint=max(sum(rc), 1))
+    owner.merge(recv_k, recv_s)
+    ok, os_, _, _, _ = owner.export()
+    # all-gather the merged, disjoint shards (variable length)
+    n_local = torch.tensor([ok.numel()], dtype=torch.int64, device=dev)
+    n_all = [torch.empty_like(n_local) for _ in range(world)]
+    dist.all_gather(n_all, n_local)
+    n_all = [int(x.item()) for x in n_all]
+    mx = max(max(n_all), 1)
+    pad_k = torch.zeros(mx, dtype=torch.int64, device=dev)
+    pad_s = torch.zeros(mx, dtype=torch.int64, device=dev)
+    pad_k[: ok.numel()] = ok
+    pad_s[: ok.numel()] = os_
+    gk = torch.empty(world * mx, dtype=torch.int64, device=dev)
+    gs = torch.empty(world * mx, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gk, pad_k)
+    dist.all_gather_into_tensor(gs, pad_s)
+    all_k = torch.cat([gk[r * mx: r * mx + n_all[r]] for r in range(world)])
+    all_s = torch.cat([gs[r * mx: r * mx + n_all[r]] for r in range(world)])
+    ns = torch.tensor([null_size], dtype=torch.int64, device=dev)
+    dist.all_reduce(ns, op=dist.ReduceOp.SUM)
+    return all_k, all_s, int(ns.item())
