@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — rows/sec through the Categorify + FillMissing + Normalize workflow
+on a synthetic Criteo-1TB-shaped table (13 int + 26 categorical columns),
+BASELINE.json configs[1] on 1 GPU and its key-hash-sharded form on N GPUs.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's engine
+    python bench.py --impl reference --gpus N ...          # the reference's CPU path (oracle port)
+
+A "step" = Workflow.fit(dataset) + Workflow.transform(dataset) over the whole
+resident table (every kernel, NCCL call and host sync of fit and transform).
+Prints ONE JSON line (see the contract in the task statement): `value` is
+device-resident throughput, `e2e` the same workflow fed from pinned HOST buffers
+with the H2D / D2H copies inside the timed region, `roofline` the dominant
+kernel against the measured HBM peak, `cpu_baseline` the CPU oracle timed on
+this box.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_ROW = 641.75      # fit 160.875 + transform 480.875 (int64 labels, f64 outputs)
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workflow(nvt, out_path, int32_outputs=False):
+    from nvtabular_b200.synth import CAT_NAMES, CONT_NAMES
+    ops = nvt.ops
+    cat_kw = {"dtype": "int32"} if int32_outputs else {}
+    norm_kw = {"out_dtype": "float32"} if int32_outputs else {}
+    cats = CAT_NAMES >> ops.Categorify(out_path=out_path, **cat_kw)
+    conts = CONT_NAMES >> ops.FillMissing() >> ops.Normalize(**norm_kw)
+    return nvt.Workflow(cats + conts + ["label"])
+
+
+def run_step(nvt, wf, frame):
+    """one pass of the hot path over the resident table: fit, then transform"""
+    ds = nvt.Dataset(frame)
+    wf.fit(ds)
+    out = None
+    for part in wf.transform(ds).partitions():
+        out = part
+    return out
+
+
+def host_copy(frame):
+    """pinned host mirror of a device frame: {name: (data, validity|None)}"""
+    import torch
+    host = {}
+    for name, c in frame.items():
+        d = torch.empty(c.data.shape, dtype=c.data.dtype, pin_memory=True)
+        d.copy_(c.data)
+        v = None
+        if c.validity is not None:
+            v = torch.empty(c.validity.shape, dtype=torch.uint8, pin_memory=True)
+            v.copy_(c.validity)
+        host[name] = (d, v)
+    return host
+
+
+def run_step_e2e(nvt, wf, host, out_host):
+    """same step from HOST buffers: H2D of every input, fit+transform, D2H of every output."""
+    import torch
+    from nvtabular_b200.column import Column, DeviceFrame
+    cols, h2d = {}, 0
+    for name, (d, v) in host.items():
+        dd = d.cuda(non_blocking=True)
+        h2d += d.numel() * d.element_size()
+        vv = None
+        if v is not None:
+            vv = v.cuda(non_blocking=True)
+            h2d += v.numel()
+        cols[name] = Column(dd, vv)
+    out = run_step(nvt, wf, DeviceFrame(cols))
+    d2h = 0
+    for name, c in out.items():
+        buf = out_host.get(name)
+        if buf is None or buf.shape != c.data.shape or buf.dtype != c.data.dtype:
+            buf = torch.empty(c.data.shape, dtype=c.data.dtype, pin_memory=True)
+            out_host[name] = buf
+        buf.copy_(c.data, non_blocking=True)
+        d2h += buf.numel() * buf.element_size()
+    torch.cuda.current_stream().synchronize()
+    return h2d, d2h
+
+
+def cpu_reference(rows, workers, seed=1234, steps=1, warmup=0):
+    """The reference's CPU path (oracle port, oracle/parallel.py) on a bounded sample of the
+    same synthetic workload.  Data is generated with torch on the CPU (same generator code)."""
+    import pandas as pd  # noqa: F401
+    from nvtabular_b200.synth import CAT_NAMES, CONT_NAMES, criteo_frame, frame_to_pandas_nullable
+    from oracle.parallel import run_criteo_workflow
+    frame = criteo_frame(rows, total_rows=rows, seed=seed, device="cpu")
+    df = frame_to_pandas_nullable(frame)
+    # what pandas itself holds for a nullable int column read from parquet: float64 + NaN
+    df = df.astype({c: "float64" for c in CAT_NAMES + CONT_NAMES})
+    times = []
+    for i in range(warmup + steps):
+        tf, tt, *_ = run_criteo_workflow(df, CAT_NAMES, CONT_NAMES, workers)
+        if i >= warmup:
+            times.append(tf + tt)
+    sec = sum(times) / len(times)
+    return rows / sec, sec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=1 << 26, help="rows resident per GPU")
+    ap.add_argument("--e2e-rows", type=int, default=0, help="rows per e2e step (default: same table)")
+    ap.add_argument("--cpu-rows", type=int, default=1 << 20, help="rows of the bounded CPU sample")
+    ap.add_argument("--int32-outputs", action="store_true", help="Categorify(dtype=int32), Normalize(float32)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = os.cpu_count() or 1
+        rows = max(args.cpu_rows * 8, 1 << 23)
+        value, sec = cpu_reference(rows, cores, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+        line = {
+            "impl": "reference", "metric": "rows/sec Criteo-1TB-shaped Categorify+FillMissing+Normalize",
+            "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "criteo-shaped 13 int + 26 cat, Categorify+FillMissing+Normalize, fit+transform",
+                       "rows_per_step": rows, "impl": "oracle port of the reference pandas path, partition-parallel"},
+            "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port",
+                             "sample": f"{rows} rows of the same synthetic table, fit+transform"},
+            "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import nvtabular_b200 as nvt
+    from nvtabular_b200 import engine
+    from nvtabular_b200.synth import criteo_frame
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    rows = args.rows
+    total_rows = rows * world
+    frame = criteo_frame(rows, total_rows=total_rows, device=dev, rank=rank)
+    out_dir = f"/tmp/nvtb_bench_rank{rank}"
+    wf = build_workflow(nvt, out_dir, args.int32_outputs)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident timing --------------------------------------
+    for _ in range(args.warmup):
+        out = run_step(nvt, wf, frame)
+        del out
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    engine.profile = []
+    launches0 = engine.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        out = run_step(nvt, wf, frame)
+        del out
+    ev1.record()
+    sync_all()
+    prof = engine.profile
+    engine.profile = None
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    launches = engine.kernel_launches - launches0
+    ms_per_step = elapsed_ms / args.steps
+    value = total_rows / (ms_per_step / 1e3)
+
+    # per-kernel-family device time (CUDA events on the launching stream)
+    fam = {}
+    for family, s, e, nbytes in prof:
+        d = fam.setdefault(family, {"ms": 0.0, "bytes": 0.0, "launches": 0})
+        d["ms"] += s.elapsed_time(e)
+        d["bytes"] += nbytes
+        d["launches"] += 1
+    peak, peak_src = _peaks()
+    kernels = {}
+    for k, d in fam.items():
+        gbs = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["ms"] > 0 else 0.0
+        kernels[k] = {"ms_per_step": d["ms"] / args.steps, "launches_per_step": d["launches"] / args.steps,
+                      "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+    dominant = max(fam, key=lambda k: fam[k]["ms"]) if fam else None
+    roofline = None
+    if dominant:
+        d = fam[dominant]
+        ach = d["bytes"] / (d["ms"] / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": d["ms"] / d["launches"],
+                    "algorithmic_bytes_per_launch": d["bytes"] / d["launches"],
+                    "share_of_step": (d["ms"] / args.steps) / ms_per_step,
+                    "whole_step_gbs": ALGO_BYTES_PER_ROW * rows / (ms_per_step / 1e3) / 1e9,
+                    "whole_step_frac": ALGO_BYTES_PER_ROW * rows / (ms_per_step / 1e3) / 1e9 / peak}
+
+    # ---------------- end to end from pinned host buffers ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        e_rows = args.e2e_rows or rows
+        src = frame if e_rows == rows else criteo_frame(e_rows, total_rows=total_rows, device=dev, rank=rank)
+        host = host_copy(src)
+        if src is not frame:
+            del src
+        out_host = {}
+        for _ in range(max(1, min(args.warmup, 2))):
+            h2d, d2h = run_step_e2e(nvt, wf, host, out_host)
+        sync_all()
+        e_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(e_steps):
+            h2d, d2h = run_step_e2e(nvt, wf, host, out_host)
+        ev1.record()
+        sync_all()
+        e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
+        t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item()) / e_steps
+        e2e = {"value": e_rows * world / (e_ms / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e_ms, "rows_per_step": e_rows * world}
+        del host, out_host
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, sec = cpu_reference(args.cpu_rows, 1)
+        cpu_baseline = {"value": v, "unit": "rows/s", "cores": 1, "kind": "port",
+                        "sample": f"{args.cpu_rows} rows of the same synthetic table, fit+transform, "
+                                  f"{sec:.1f} s on 1 core (host has {os.cpu_count()})"}
+
+    line = {
+        "metric": "rows/sec Criteo-1TB-shaped Categorify+FillMissing+Normalize",
+        "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64" if not args.int32_outputs else "int32", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1]: Criteo-1TB-shaped synthetic (13 int + 26 cat int32, "
+                               "nullable), Categorify+FillMissing+Normalize, one step = Workflow.fit + "
+                               "Workflow.transform over the HBM-resident table",
+                   "rows_per_gpu": rows, "total_rows": total_rows,
+                   "outputs": "int32 labels, float32 conts" if args.int32_outputs else "int64 labels, float64 conts",
+                   "algorithmic_bytes_per_row": ALGO_BYTES_PER_ROW if not args.int32_outputs else 485.75,
+                   "cache": "inputs (%.1f GB/GPU) larger than L2; no explicit flush" % (rows * 160.9 / 1e9),
+                   "parallelism": f"row-sharded x{world}, key-hash owner merge over NCCL" if world > 1 else "single GPU"},
+        "roofline": roofline, "kernels": kernels, "e2e": e2e, "cpu_baseline": cpu_baseline,
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -49,7 +49,9 @@ typedef enum {
   NVTB_I64 = 1,
   NVTB_F32 = 2,
   NVTB_F64 = 3,
-  NVTB_U8 = 4 /* bool / fold ids */
+  NVTB_U8 = 4,  /* bool / fold ids */
+  NVTB_H64 = 5  /* hash columns only: a precomputed 64-bit value hash (e.g. the
+                   pandas string hash of a dictionary entry), used as-is   */
 } nvtb_dtype_t;
 
 typedef struct {

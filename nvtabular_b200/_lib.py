@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libnvtb200.so")
 
 # nvtb_dtype_t
-I32, I64, F32, F64, U8 = 0, 1, 2, 3, 4
+I32, I64, F32, F64, U8, H64 = 0, 1, 2, 3, 4, 5
 
 
 class NvtbError(RuntimeError):

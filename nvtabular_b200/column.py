@@ -63,7 +63,7 @@ class Column:
                 consumes the column), else None
     """
 
-    __slots__ = ("data", "validity", "offsets", "dictionary", "fill", "is_bool")
+    __slots__ = ("data", "validity", "offsets", "dictionary", "fill", "is_bool", "prehashed")
 
     def __init__(self, data, validity=None, offsets=None, dictionary=None, fill=None, is_bool=False):
         if data.dtype == torch.bool:
@@ -75,6 +75,7 @@ class Column:
         self.dictionary = dictionary
         self.fill = fill
         self.is_bool = is_bool
+        self.prehashed = False   # int64 data that already IS a value hash (NVTB_H64)
 
     # ------------------------------------------------------------------ meta
     @property
@@ -94,6 +95,8 @@ class Column:
 
     @property
     def dtype_code(self) -> int:
+        if self.prehashed:
+            return _lib.H64
         return _TORCH2CODE[self.data.dtype]
 
     @property

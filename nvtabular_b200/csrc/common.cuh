@@ -60,6 +60,7 @@ inline size_t dtype_size(int dt) {
     case NVTB_F32: return 4;
     case NVTB_F64: return 8;
     case NVTB_U8: return 1;
+    case NVTB_H64: return 8;
     default: return 0;
   }
 }

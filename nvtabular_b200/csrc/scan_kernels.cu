@@ -302,6 +302,7 @@ __device__ __forceinline__ uint64_t hash_one(const HashCols& hc, int c,
       case NVTB_I64: bits = value_bits<int64_t>(((const int64_t*)hc.data[c])[i]); break;
       case NVTB_F32: bits = value_bits<float>(((const float*)hc.data[c])[i]); break;
       case NVTB_F64: bits = value_bits<double>(((const double*)hc.data[c])[i]); break;
+      case NVTB_H64: return (uint64_t)((const int64_t*)hc.data[c])[i];  // already a hash
       default:       bits = value_bits<uint8_t>(((const uint8_t*)hc.data[c])[i]); break;
     }
   }
@@ -517,14 +518,14 @@ int nvtb_hash_bucket_apply(const nvtb_col_t* cols, int ncols, int64_t n,
                "out_dtype must be int32 or int64");
   NVTB_REQUIRE(n >= 0 && cols != nullptr, "bad n/cols");
   for (int c = 0; c < ncols; ++c)
-    NVTB_REQUIRE(cols[c].dtype >= NVTB_I32 && cols[c].dtype <= NVTB_U8 &&
+    NVTB_REQUIRE(cols[c].dtype >= NVTB_I32 && cols[c].dtype <= NVTB_H64 &&
                      (n == 0 || cols[c].data),
                  "bad hash column");
   if (n == 0) return NVTB_OK;
   NVTB_REQUIRE(out != nullptr, "out is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = scan_grid(n, 8);
-  if (ncols == 1 && cols[0].dtype != NVTB_U8) {
+  if (ncols == 1 && cols[0].dtype <= NVTB_F64) {
     if (out_dtype == NVTB_I32)
       hash_bucket1_kernel<int32_t><<<grid, kThreads, 0, st>>>(
           cols[0].data, cols[0].validity, cols[0].dtype, (int32_t*)out, n, num_buckets, add);
@@ -549,7 +550,7 @@ int nvtb_hash_bucket_apply(const nvtb_col_t* cols, int ncols, int64_t n,
 
 int nvtb_hash_values(const nvtb_col_t* col, int64_t n, uint64_t* out, void* stream) {
   NVTB_REQUIRE(col != nullptr && n >= 0, "bad col/n");
-  NVTB_REQUIRE(col->dtype >= NVTB_I32 && col->dtype <= NVTB_U8, "bad dtype");
+  NVTB_REQUIRE(col->dtype >= NVTB_I32 && col->dtype <= NVTB_H64, "bad dtype");
   if (n == 0) return NVTB_OK;
   NVTB_REQUIRE(col->data && out, "NULL data/out");
   HashCols hc;

@@ -106,6 +106,7 @@ __device__ __forceinline__ uint64_t hash_cols_at(const HashCols& hc, int64_t i) 
         case NVTB_I64: bits = value_bits<int64_t>(((const int64_t*)hc.data[c])[i]); break;
         case NVTB_F32: bits = value_bits<float>(((const float*)hc.data[c])[i]); break;
         case NVTB_F64: bits = value_bits<double>(((const double*)hc.data[c])[i]); break;
+        case NVTB_H64: h ^= (uint64_t)((const int64_t*)hc.data[c])[i]; continue;  // already a hash
         default:       bits = value_bits<uint8_t>(((const uint8_t*)hc.data[c])[i]); break;
       }
     }
@@ -382,7 +383,7 @@ int nvtb_encode_apply(const nvtb_vocab_t* v, const nvtb_col_t* key, int64_t n,
   memset(&hc, 0, sizeof(hc));
   hc.ncols = n_hash_cols;
   for (int c = 0; c < n_hash_cols; ++c) {
-    NVTB_REQUIRE(hash_cols[c].data != nullptr && hash_cols[c].dtype >= NVTB_I32 && hash_cols[c].dtype <= NVTB_U8,
+    NVTB_REQUIRE(hash_cols[c].data != nullptr && hash_cols[c].dtype >= NVTB_I32 && hash_cols[c].dtype <= NVTB_H64,
                  "bad hash column");
     hc.data[c] = hash_cols[c].data; hc.mask[c] = hash_cols[c].validity; hc.dtype[c] = hash_cols[c].dtype;
   }

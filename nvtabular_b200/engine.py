@@ -29,6 +29,36 @@ def _count(n=1):
     kernel_launches += n
 
 
+# --- optional per-kernel-family device timing (bench.py's roofline object) -----
+# When `profile` is a list, every wrapper below brackets its launch with CUDA
+# events on the launching stream and appends (family, start, end, algorithmic
+# bytes).  Events are only read after the timed region has been synchronised.
+profile = None
+
+
+class _timed:
+    def __init__(self, family: str, nbytes: float):
+        self.family, self.nbytes = family, nbytes
+
+    def __enter__(self):
+        if profile is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if profile is not None:
+            self.e.record()
+            profile.append((self.family, self.s, self.e, self.nbytes))
+        return False
+
+
+def _in_bytes(cols) -> float:
+    """algorithmic read bytes: data + 1 validity bit per row."""
+    return float(sum(c.data.numel() * (c.data.element_size() + 0.125) for c in cols))
+
+
 def dtype_code(dt) -> int:
     if isinstance(dt, torch.dtype):
         return {v: k for k, v in _CODE2TORCH.items()}[dt]
@@ -71,8 +101,9 @@ class Moments:
     def accumulate(self, cols: Sequence[Column]):
         assert len(cols) == self.ncols
         n = _check_same_len(cols)
-        _lib.check(self.lib.nvtb_moments_accumulate(
-            _descs(cols), self.ncols, n, _fills(cols), _ptr(self.acc), _lib.stream_ptr()))
+        with _timed("moments", _in_bytes(cols)):
+            _lib.check(self.lib.nvtb_moments_accumulate(
+                _descs(cols), self.ncols, n, _fills(cols), _ptr(self.acc), _lib.stream_ptr()))
         _count(2)
 
     def allreduce(self):
@@ -133,9 +164,10 @@ def normalize_apply(cols: Sequence[Column], means, stds, out_dtype=np.float64):
     n = _check_same_len(cols)
     code = dtype_code(out_dtype)
     outs = _alloc_like(cols, _CODE2TORCH[code])
-    _lib.check(lib.nvtb_normalize_apply(
-        _descs(cols), len(cols), n, _fills(cols), _lib.double_array(means), _lib.double_array(stds),
-        _lib.ptr_array([o.data_ptr() for o in outs]), code, _lib.stream_ptr()))
+    with _timed("normalize", _in_bytes(cols) + sum(o.numel() * o.element_size() for o in outs)):
+        _lib.check(lib.nvtb_normalize_apply(
+            _descs(cols), len(cols), n, _fills(cols), _lib.double_array(means), _lib.double_array(stds),
+            _lib.ptr_array([o.data_ptr() for o in outs]), code, _lib.stream_ptr()))
     _count()
     return [Column(o, None if c.fill is not None else c.validity, c.offsets) for o, c in zip(outs, cols)]
 
@@ -160,8 +192,9 @@ def hash_bucket(cols: Sequence[Column], num_buckets: int, add: int = 0, out_dtyp
     n = _check_same_len(cols)
     code = dtype_code(out_dtype)
     out = torch.empty(n, dtype=_CODE2TORCH[code], device=cols[0].data.device)
-    _lib.check(lib.nvtb_hash_bucket_apply(_descs(cols), len(cols), n, int(num_buckets), int(add),
-                                          _ptr(out), code, _lib.stream_ptr()))
+    with _timed("hash_bucket", _in_bytes(cols) + out.numel() * out.element_size()):
+        _lib.check(lib.nvtb_hash_bucket_apply(_descs(cols), len(cols), n, int(num_buckets), int(add),
+                                              _ptr(out), code, _lib.stream_ptr()))
     _count()
     return out
 
@@ -224,8 +257,9 @@ class HashAgg:
         assert len(agg_cols) == self.n_agg
         for c in agg_cols:
             assert c.data.numel() == n
-        _lib.check(self.lib.nvtb_hashagg_insert(
-            self.h, _descs([key]), _descs(agg_cols) if self.n_agg else None, n, _lib.stream_ptr()))
+        with _timed("hashagg_insert", _in_bytes([key]) + _in_bytes(agg_cols)):
+            _lib.check(self.lib.nvtb_hashagg_insert(
+                self.h, _descs([key]), _descs(agg_cols) if self.n_agg else None, n, _lib.stream_ptr()))
         _count(max(1, (n + (1 << 23) - 1) >> 23))
 
     def merge(self, keys: torch.Tensor, sizes: torch.Tensor, vals: Optional[torch.Tensor] = None):
@@ -250,8 +284,9 @@ class HashAgg:
         sizes = torch.empty(nu, dtype=torch.int64, device=device)
         vals = torch.empty((nu, self.n_agg, 4), dtype=torch.float64, device=device) if self.n_agg else None
         null_vals = (ctypes.c_double * (4 * max(self.n_agg, 1)))()
-        _lib.check(self.lib.nvtb_hashagg_export(self.h, _ptr(keys), _ptr(sizes), _ptr(vals),
-                                                null_vals if self.n_agg else None, _lib.stream_ptr()))
+        with _timed("hashagg_export", float(nu * 16)):
+            _lib.check(self.lib.nvtb_hashagg_export(self.h, _ptr(keys), _ptr(sizes), _ptr(vals),
+                                                    null_vals if self.n_agg else None, _lib.stream_ptr()))
         _count()
         nv = np.array(list(null_vals), dtype=np.float64).reshape(-1, 4)[: self.n_agg] if self.n_agg else None
         return keys, sizes, vals, ns, nv
@@ -303,9 +338,10 @@ class Vocab:
         _lib.require_cuda()
         lib = _lib.load()
         h = c_void_p()
-        _lib.check(lib.nvtb_vocab_build(byref(h), _ptr(keys), _ptr(sizes), keys.numel(), int(null_size),
-                                        int(freq_threshold or 0), int(max_size or 0), int(num_buckets or 0),
-                                        _lib.stream_ptr()))
+        with _timed("vocab_build", float(keys.numel() * 16)):
+            _lib.check(lib.nvtb_vocab_build(byref(h), _ptr(keys), _ptr(sizes), keys.numel(), int(null_size),
+                                            int(freq_threshold or 0), int(max_size or 0), int(num_buckets or 0),
+                                            _lib.stream_ptr()))
         _count(8)
         return cls(h, lib)
 
@@ -337,10 +373,11 @@ class Vocab:
         n = key.data.numel()
         code = dtype_code(out_dtype)
         out = torch.empty(n, dtype=_CODE2TORCH[code], device=key.data.device)
-        _lib.check(self.lib.nvtb_encode_apply(
-            self.h, _descs([key]), n, int(null_label), int(oov_label), int(first_label),
-            int(num_buckets or 0), _descs(hash_cols) if hash_cols else None, len(hash_cols),
-            _ptr(out), code, _lib.stream_ptr()))
+        with _timed("encode", _in_bytes([key]) + out.numel() * out.element_size()):
+            _lib.check(self.lib.nvtb_encode_apply(
+                self.h, _descs([key]), n, int(null_label), int(oov_label), int(first_label),
+                int(num_buckets or 0), _descs(hash_cols) if hash_cols else None, len(hash_cols),
+                _ptr(out), code, _lib.stream_ptr()))
         _count()
         return out
 

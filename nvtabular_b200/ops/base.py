@@ -10,7 +10,14 @@ from ..column import Column, DeviceFrame
 from ..graph import ColumnSchema, ColumnSelector, Schema
 
 
-class Operator:
+class _OperatorMeta(type):
+    """lets an operator CLASS stand on the right of `>>` (`cols >> ops.Categorify`)."""
+
+    def __rrshift__(cls, other):
+        return ColumnSelector(other) >> cls()
+
+
+class Operator(metaclass=_OperatorMeta):
     #: ops that consume a deferred FillMissing inside their own kernel
     fuses_fill = False
 

@@ -64,6 +64,11 @@ class FittedVocab:
     def n_kept(self):
         return self.vocab.n_kept
 
+    @property
+    def file_rows(self):
+        """rows of unique.<name>.parquet (an empty input writes one null row)"""
+        return 1 if self.vocab.n_total == 0 else self.vocab.n_kept
+
     def unique_frame(self) -> pd.DataFrame:
         keys, sizes = self.vocab.export(with_sizes=self.has_sizes)
         k = keys.cpu().numpy()
@@ -97,7 +102,7 @@ class FittedVocab:
         self.meta_frame().to_parquet(meta_path)
         if force or self.vocab.n_kept <= EAGER_ARTIFACT_ROWS:
             df = self.unique_frame()
-            if len(df) == 0:   # categorify.py:1318-1324: a single null row
+            if self.vocab.n_total == 0:   # categorify.py:1318-1324: empty input -> a single null row
                 df = pd.DataFrame({n: pd.Series([None], dtype=object) for n in self.key_names})
             df.to_parquet(self.path, compression=None)
             self._written = True
@@ -320,7 +325,7 @@ class Categorify(StatOperator):
         for name, fv in merged.items():
             if self.single_table:                      # categorify.py:410-415, 1884-1897
                 fv.index_start = fv.index_start + idx_count
-                idx_count += max(fv.n_kept, 1) if fv.n_kept == 0 else fv.n_kept
+                idx_count += fv.file_rows
                 fv._written = False
             if name in categories or self.single_table:
                 fv.write(base)
@@ -436,7 +441,7 @@ class Categorify(StatOperator):
             num_rows = OOV_OFFSET
             fv = self.categories.fitted.get(col)
             if fv is not None:
-                num_rows += max(fv.n_kept, 1) if fv.n_kept == 0 else fv.n_kept
+                num_rows += fv.file_rows
             if isinstance(buckets, dict):
                 bucket_size = buckets.get(col, 0)
             else:
@@ -482,49 +487,8 @@ def _parse_bytes(v):
 
 
 def _global_unique_merge(agg: engine.HashAgg):
-    """Local table -> globally merged (keys, sizes, null_size), identical on every rank.
-
-    Multi-GPU: (key, size) rows are routed to owner =
-    mix(key) % world with one all-to-all, each owner merges its shard (exact
-    global counts, disjoint keys), and the shards are all-gathered so every rank
-    can build the same vocabulary.  Replaces the dask tree reduce + filesystem
-    "broadcast" of categorify.py:1399-1540, 1627-1643."""
-    import torch.distributed as dist
-    keys, sizes, _, null_size, _ = agg.export()
-    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-        return keys, sizes, null_size
-    world = dist.get_world_size()
-    dev = keys.device
-    perm, counts = engine.partition_by_owner(keys, world)
-    send_k = engine.gather_i64(keys, perm)
-    send_s = engine.gather_i64(sizes, perm)
-    send_counts = torch.tensor(counts, dtype=torch.int64, device=dev)
-    recv_counts = torch.empty_like(send_counts)
-    dist.all_to_all_single(recv_counts, send_counts)
-    rc = [int(x) for x in recv_counts.cpu().tolist()]
-    recv_k = torch.empty(sum(rc), dtype=torch.int64, device=dev)
-    recv_s = torch.empty(sum(rc), dtype=torch.int64, device=dev)
-    dist.all_to_all_single(recv_k, send_k, output_split_sizes=rc, input_split_sizes=counts)
-    dist.all_to_all_single(recv_s, send_s, output_split_sizes=rc, input_split_sizes=counts)
-    owner = engine.HashAgg(0, capacity_hint=max(sum(rc), 1))
-    owner.merge(recv_k, recv_s)
-    ok, os_, _, _, _ = owner.export()
-    # all-gather the merged, disjoint shards (variable length)
-    n_local = torch.tensor([ok.numel()], dtype=torch.int64, device=dev)
-    n_all = [torch.empty_like(n_local) for _ in range(world)]
-    dist.all_gather(n_all, n_local)
-    n_all = [int(x.item()) for x in n_all]
-    mx = max(max(n_all), 1)
-    pad_k = torch.zeros(mx, dtype=torch.int64, device=dev)
-    pad_s = torch.zeros(mx, dtype=torch.int64, device=dev)
-    pad_k[: ok.numel()] = ok
-    pad_s[: ok.numel()] = os_
-    gk = torch.empty(world * mx, dtype=torch.int64, device=dev)
-    gs = torch.empty(world * mx, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(gk, pad_k)
-    dist.all_gather_into_tensor(gs, pad_s)
-    all_k = torch.cat([gk[r * mx: r * mx + n_all[r]] for r in range(world)])
-    all_s = torch.cat([gs[r * mx: r * mx + n_all[r]] for r in range(world)])
-    ns = torch.tensor([null_size], dtype=torch.int64, device=dev)
-    dist.all_reduce(ns, op=dist.ReduceOp.SUM)
-    return all_k, all_s, int(ns.item())
+    """Local table -> globally merged (keys, sizes, null_size), identical on every
+    rank (single GPU: a plain export).  See nvtabular_b200/dist.py."""
+    from ..dist import global_merge
+    keys, sizes, _, null_size, _ = global_merge(agg)
+    return keys, sizes, null_size

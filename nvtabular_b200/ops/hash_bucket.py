@@ -25,7 +25,9 @@ def string_hash_column(col: Column) -> Column:
         else np.zeros(0, dtype=np.int64)
     table = torch.from_numpy(h.copy()).to(col.data.device)
     idx = col.data.to(torch.int64).clamp_(0, max(len(h) - 1, 0))
-    return Column(table[idx] if len(h) else torch.zeros_like(idx), col.validity, col.offsets)
+    out = Column(table[idx] if len(h) else torch.zeros_like(idx), col.validity, col.offsets)
+    out.prehashed = True
+    return out
 
 
 class HashBucket(Operator):
@@ -43,10 +45,9 @@ class HashBucket(Operator):
         for col, nb in num_buckets.items():
             c = self._get(df, col)
             if c.is_string:
-                raise NotImplementedError(
-                    "HashBucket on string columns: hash the dictionary on the host first "
-                    "(string keys are outside the B200 hot path)")
-            leaf = Column(c.data, c.validity, None, None, None, c.is_bool)
+                leaf = string_hash_column(Column(c.data, c.validity, None, c.dictionary))
+            else:
+                leaf = Column(c.data, c.validity, None, None, None, c.is_bool)
             out = engine.hash_bucket([leaf], nb, 0, np.int32)
             df[col] = Column(out, None, c.offsets)
         return df

@@ -1,0 +1,101 @@
+"""world_size-2 gloo worker for tests/test_dist_cpu.py: runs the product's exchange
+code (nvtabular_b200.dist.global_merge, engine.Moments.allreduce arithmetic) with a
+numpy stand-in for the CUDA kernels, and writes each rank's result to disk."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _mix(k):
+    k = np.asarray(k).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        k ^= k >> np.uint64(33); k *= np.uint64(0xFF51AFD7ED558CCD)
+        k ^= k >> np.uint64(33); k *= np.uint64(0xC4CEB9FE1A85EC53)
+        k ^= k >> np.uint64(33)
+    return k
+
+
+class FakeAgg:
+    """host stand-in for engine.HashAgg (TEST ONLY)."""
+
+    def __init__(self, n_agg=0, capacity_hint=0):
+        self.n_agg = n_agg
+        self.table = {}
+        self.null_size = 0
+        self.null_vals = np.tile(np.array([0.0, 0.0, np.nan, np.nan]), (max(n_agg, 1), 1))[:n_agg] if n_agg else None
+
+    def merge(self, keys, sizes, vals=None):
+        v = vals.reshape(-1, self.n_agg, 4).numpy() if vals is not None else None
+        for i, (k, s) in enumerate(zip(keys.tolist(), sizes.tolist())):
+            cur = self.table.get(k)
+            if cur is None:
+                self.table[k] = [s, v[i].copy() if v is not None else None]
+            else:
+                cur[0] += s
+                if v is not None:
+                    cur[1][:, 0:2] += v[i][:, 0:2]
+                    cur[1][:, 2] = np.fmin(cur[1][:, 2], v[i][:, 2])
+                    cur[1][:, 3] = np.fmax(cur[1][:, 3], v[i][:, 3])
+
+    def export(self):
+        keys = torch.tensor(list(self.table.keys()), dtype=torch.int64)
+        sizes = torch.tensor([v[0] for v in self.table.values()], dtype=torch.int64)
+        vals = torch.tensor(np.stack([v[1] for v in self.table.values()]), dtype=torch.float64) \
+            if self.n_agg and self.table else (torch.zeros((0, self.n_agg, 4), dtype=torch.float64) if self.n_agg else None)
+        return keys, sizes, vals, self.null_size, self.null_vals
+
+
+class FakeEngine:
+    HashAgg = FakeAgg
+
+    @staticmethod
+    def partition_by_owner(keys, n_parts):
+        owner = ((_mix(keys.numpy()) >> np.uint64(52)) % np.uint64(n_parts)).astype(np.int64)
+        perm = np.argsort(owner, kind="stable")
+        return torch.from_numpy(perm), [int((owner == p).sum()) for p in range(n_parts)]
+
+    @staticmethod
+    def gather_i64(src, perm):
+        return src[perm]
+
+    @staticmethod
+    def gather_f64_rows(src, perm, width):
+        return src[perm]
+
+
+def main():
+    out_dir = sys.argv[1]
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    from nvtabular_b200.dist import allgather_var, global_merge
+    rng = np.random.default_rng(100 + rank)
+    # each rank saw different rows: overlapping key sets, different counts
+    keys = rng.integers(0, 500, 3000)
+    x = rng.standard_normal(3000)
+    agg = FakeAgg(1)
+    for k, v in zip(keys.tolist(), x.tolist()):
+        agg.merge(torch.tensor([k]), torch.tensor([1]), torch.tensor([[v, v * v, v, v]], dtype=torch.float64))
+    agg.null_size = 7 + rank
+    agg.null_vals = np.array([[1.0 + rank, 2.0, -3.0 - rank, 4.0 + rank]])
+    k, s, v, ns, nv = global_merge(agg, engine=FakeEngine)
+    order = np.argsort(k.numpy())
+    res = {"keys": k.numpy()[order].tolist(), "sizes": s.numpy()[order].tolist(),
+           "vals": v.numpy()[order].reshape(len(order), -1).tolist(), "null_size": ns, "null_vals": nv.tolist(),
+           "local_keys": keys.tolist(), "local_x": x.tolist()}
+    t = allgather_var(torch.arange(rank + 2, dtype=torch.int64))
+    res["allgather_var"] = t.tolist()
+    with open(os.path.join(out_dir, f"rank{rank}.json"), "w") as f:
+        json.dump(res, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,153 @@
+"""CPU tests: operator-graph sugar, column model, dataset partitioning, the C-ABI
+library (loads, exports every declared symbol — no compute calls without a GPU),
+and the rule that the product never touches the oracle or a CPU fallback."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from nvtabular_b200 import _build, _lib
+    _build.build()
+    header = open(os.path.join(ROOT, "include", "nvtb200.h")).read()
+    declared = set(re.findall(r"\b(nvtb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed from include/nvtb200.h"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libnvtb200.so does not export {name}"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert _lib.load().nvtb_version() >= 1
+
+
+def test_library_targets_sm100a_with_256bit_accesses():
+    from nvtabular_b200 import _lib
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass or "SM100a" in sass.upper() or "sm_100" in sass
+    assert re.search(r"LDG\.E[.\w]*\.256", sass) and re.search(r"STG\.E[.\w]*\.256", sass)
+
+
+def test_product_never_imports_oracle_or_reference():
+    bad = []
+    for base, _, files in os.walk(os.path.join(ROOT, "nvtabular_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(base, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "/root/reference" in src:
+                    bad.append(os.path.join(base, f))
+    assert not bad, bad
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import nvtabular as nvt
+    from nvtabular_b200._lib import NvtbError
+    df = pd.DataFrame({"a": [1, 2, 2], "x": [1.0, np.nan, 3.0]})
+    wf = nvt.Workflow((["a"] >> nvt.ops.Categorify()) + (["x"] >> nvt.ops.FillMissing() >> nvt.ops.Normalize()))
+    with pytest.raises(NvtbError):
+        wf.fit(nvt.Dataset(df))
+
+
+def test_column_selector_and_node_sugar():
+    import nvtabular as nvt
+    from nvtabular import ColumnSelector, ops
+    sel = ColumnSelector(["a", ["b", "c"]])
+    assert sel.names == ["a", "b", "c"] and sel.grouped_names == ["a", ("b", "c")]
+    with pytest.raises(ValueError):
+        ColumnSelector([["a", ["b"]]])
+    node = ["a", ["b", "c"]] >> ops.Categorify(encode_type="combo")
+    assert node.output_columns.names == ["a", "b_c"]
+    joint = [["b", "c"]] >> ops.Categorify()
+    assert joint.output_columns.names == ["b", "c"]
+    conts = ["x", "y"] >> ops.FillMissing(add_binary_cols=True) >> ops.Normalize()
+    assert conts.output_columns.names == ["x", "y", "x_filled", "y_filled"]
+    both = node + conts + "label"
+    assert both.output_columns.names == ["a", "b_c", "x", "y", "x_filled", "y_filled", "label"]
+    assert (both - ["label"]).output_columns.names == ["a", "b_c", "x", "y", "x_filled", "y_filled"]
+    assert both[["a", "x"]].output_columns.names == ["a", "x"]
+    assert nvt.Workflow(both).output_node.root_columns() == ["a", "b", "c", "x", "y", "label"]
+    as_class = ["a"] >> ops.Categorify          # ops may be passed as classes
+    assert isinstance(as_class.op, ops.Categorify)
+    jg = ["u", ["u", "m"]] >> ops.JoinGroupby(cont_cols=["r"], stats=["count", "sum"])
+    assert jg.output_columns.names == ["u_count", "u_r_sum", "u_m_count", "u_m_r_sum"]
+    te = ["u", ["u", "m"]] >> ops.TargetEncoding("r", kfold=3, drop_folds=False)
+    assert te.output_columns.names == ["TE_u_r", "TE_u_m_r", "__fold__"]
+    with pytest.raises(ValueError):
+        ops.JoinGroupby(cont_cols=["r"], stats=["median"])
+    with pytest.raises(TypeError):
+        ops.HashBucket("ten")
+
+
+def test_categorify_kwarg_validation():
+    from nvtabular import ops
+    for bad in (dict(start_index=1), dict(na_sentinel=0), dict(bogus=1), dict(encode_type="x"),
+                dict(num_buckets=0), dict(freq_threshold=1, max_size=5), dict(search_sorted=True, freq_threshold=2),
+                dict(encode_type="combo", vocabs={"a": pd.Series([1])}), dict(num_buckets=1.5), dict(max_size="3")):
+        with pytest.raises(ValueError):
+            ops.Categorify(**bad)
+    with pytest.warns(UserWarning):
+        ops.Categorify(num_buckets=10)
+    with pytest.warns(FutureWarning):
+        ops.Categorify(tree_width=4)
+    assert ops.Categorify().output_dtype == np.int64 and ops.Categorify(dtype=np.int32).output_dtype == np.int32
+    assert ops.emb_sz_rule(29) == (29, 16)
+
+
+def test_column_roundtrip_and_bitmask():
+    from nvtabular_b200.column import Column, DeviceFrame, pack_validity, unpack_validity
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 8, 9, 255, 1000):
+        v = torch.from_numpy(rng.random(n) < 0.5)
+        m = pack_validity(v)
+        assert m.numel() % 32 == 0 and torch.equal(unpack_validity(m, n), v)
+        if n:   # Arrow layout: bit (i & 7) of byte (i >> 3)
+            i = n - 1
+            assert bool((int(m[i >> 3]) >> (i & 7)) & 1) == bool(v[i])
+    df = pd.DataFrame({
+        "i": pd.array([1, None, 3], dtype="Int32"), "f": [1.5, np.nan, 2.5], "s": ["b", None, "a"],
+        "l": [[1, 2], [], [3]], "b": [True, False, True], "u": np.array([1, 2, 3], dtype="uint16"),
+    })
+    fr = DeviceFrame.from_pandas(df, device="cpu")
+    assert fr["i"].data.dtype == torch.int32 and fr["i"].null_count() == 1
+    assert fr["s"].dictionary.tolist() == ["a", "b"] and fr["s"].data.tolist()[0] == 1
+    assert fr["l"].offsets.tolist() == [0, 2, 2, 3] and fr["u"].data.dtype == torch.int32
+    back = pd.DataFrame({k: c.to_pandas(k) for k, c in fr.items()})
+    assert back["i"].tolist()[0] == 1 and np.isnan(back["i"].tolist()[1])
+    assert back["s"].tolist()[0] == "b" and back["s"].isna().tolist() == [False, True, False]
+    assert [list(x) for x in back["l"]] == [[1, 2], [], [3]] and back["b"].tolist() == [True, False, True]
+
+
+def test_dataset_partitions_like_dask_from_pandas():
+    import nvtabular as nvt
+    df = pd.DataFrame({"a": np.arange(26)})
+    ds = nvt.Dataset(df, npartitions=3, device="cpu")
+    assert [len(p) for p in ds.partitions()] == [9, 9, 8]
+    assert ds.num_rows == 26 and ds.schema.column_names == ["a"]
+    assert ds.to_ddf().compute()["a"].tolist() == list(range(26))
+
+
+def test_keyspace_string_and_float_keys_are_order_preserving():
+    from nvtabular_b200.column import Column
+    from nvtabular_b200.ops.keyspace import KeySpace, _float_to_key, _key_to_float
+    a = Column.from_strings(["pear", "apple", None, "fig"], device="cpu")
+    b = Column.from_strings(["kiwi", "apple"], device="cpu")
+    ks = KeySpace.for_columns([a, b])
+    assert ks.dictionary.tolist() == ["apple", "fig", "kiwi", "pear"]
+    assert ks.keys_for(a).data.tolist() == [3, 0, 0, 1] and ks.keys_for(b).data.tolist() == [2, 0]
+    unseen = Column.from_strings(["zzz", "apple", "aaa"], device="cpu")
+    k = ks.keys_for(unseen).data.tolist()
+    assert k[1] == 0 and k[0] < 0 and k[2] < 0 and k[0] != k[2]
+    assert ks.decode(np.array([0, 3])).tolist() == ["apple", "pear"]
+    x = np.array([-1e300, -2.5, -0.0, 0.0, 1e-300, 3.0, np.inf])
+    key = _float_to_key(Column(torch.from_numpy(x))).data.numpy()
+    assert (np.diff(key) >= 0).all() and key[2] == key[3]
+    np.testing.assert_array_equal(_key_to_float(key), np.where(x == 0, 0.0, x))
