@@ -172,7 +172,12 @@ def main():
     ap.add_argument("--int32-outputs", action="store_true", help="Categorify(dtype=int32), Normalize(float32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--eager-artifacts", action="store_true",
+                    help="write the vocabulary parquet files inside fit (default: deferred until read)")
+    ap.add_argument("--pyprofile", action="store_true", help="cProfile one extra step to stderr")
     args = ap.parse_args()
+    if not args.eager_artifacts:
+        os.environ["NVTB_ARTIFACTS"] = "lazy"
     args.warmup = max(args.warmup, 0)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -222,6 +227,18 @@ def main():
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    if args.pyprofile and rank == 0:
+        import cProfile
+        import pstats
+        run_step(nvt, wf, frame)
+        torch.cuda.synchronize()
+        pr = cProfile.Profile()
+        pr.enable()
+        run_step(nvt, wf, frame)
+        torch.cuda.synchronize()
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(35)
 
     # ---------------- device-resident timing --------------------------------------
     for _ in range(args.warmup):
@@ -332,6 +349,8 @@ def main():
                    "outputs": "int32 labels, float32 conts" if args.int32_outputs else "int64 labels, float64 conts",
                    "algorithmic_bytes_per_row": ALGO_BYTES_PER_ROW if not args.int32_outputs else 485.75,
                    "cache": "inputs (%.1f GB/GPU) larger than L2; no explicit flush" % (rows * 160.9 / 1e9),
+                   "artifacts": "eager" if args.eager_artifacts else
+                                "unique./meta. parquet files deferred until read (NVTB_ARTIFACTS=lazy)",
                    "parallelism": f"row-sharded x{world}, key-hash owner merge over NCCL" if world > 1 else "single GPU"},
         "roofline": roofline, "kernels": kernels, "e2e": e2e, "cpu_baseline": cpu_baseline,
         "gpu_launches": launches, "clocks": clocks,

@@ -149,7 +149,10 @@ int nvtb_hash_values(const nvtb_col_t* col_host, int64_t n, uint64_t* out,
  *   per cont column: sum / sumsq over non-null values, min, max
  *           (NaN when the group has no non-null value).
  *
- * n_agg = number of continuous columns (0 for Categorify).
+ * n_agg = number of continuous columns (0 for Categorify).  capacity_hint =
+ * expected number of distinct keys (0 = unknown: the first 2^20 rows are
+ * inserted on their own and their exact distinct count sizes the table).
+ * The hint only affects speed; results never depend on it.
  * key dtype I32 or I64 (multi-column keys are packed to I64 with
  * nvtb_pack_keys2 first).
  */
@@ -157,8 +160,12 @@ typedef struct nvtb_hashagg nvtb_hashagg_t;
 int nvtb_hashagg_create(nvtb_hashagg_t** out, int n_agg,
                         int64_t capacity_hint);
 int nvtb_hashagg_destroy(nvtb_hashagg_t* h);
-/* insert one batch of raw rows; agg_cols_host may be NULL when n_agg == 0.
- * Synchronises the stream only when the table has to grow. */
+/* empty the table but keep its capacity and cardinality estimate (a second fit
+ * over similar data then needs neither growth nor the sampling pass) */
+int nvtb_hashagg_reset(nvtb_hashagg_t* h, void* stream);
+/* insert one batch of raw rows (one kernel launch); agg_cols_host may be NULL
+ * when n_agg == 0.  Waits for the handle's PREVIOUS launch (its counters are
+ * read back), never for the one it enqueues. */
 int nvtb_hashagg_insert(nvtb_hashagg_t* h, const nvtb_col_t* key_host,
                         const nvtb_col_t* agg_cols_host, int64_t n,
                         void* stream);

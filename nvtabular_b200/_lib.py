@@ -46,6 +46,7 @@ _SIGNATURES = {
     "nvtb_hash_values": (c_int, [POINTER(nvtb_col_t), c_int64, c_void_p, c_void_p]),
     "nvtb_hashagg_create": (c_int, [POINTER(c_void_p), c_int, c_int64]),
     "nvtb_hashagg_destroy": (c_int, [c_void_p]),
+    "nvtb_hashagg_reset": (c_int, [c_void_p, c_void_p]),
     "nvtb_hashagg_insert": (c_int, [c_void_p, POINTER(nvtb_col_t), POINTER(nvtb_col_t), c_int64, c_void_p]),
     "nvtb_hashagg_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "nvtb_hashagg_add_null_group": (c_int, [c_void_p, c_int64, POINTER(c_double)]),

@@ -3,26 +3,33 @@
 // Replaces the reference's per-partition cuDF groupby + concat/groupby tree
 // (nvtabular/ops/categorify.py:955-1137, graph built at :1344-1540) with ONE
 // resident open-addressing table per column group that every batch is folded
-// into.  Design (B200-first, not a translation of cuDF's groupby):
+// into.  Design (B200-first, not a translation of cuDF's groupby, which sizes a
+// fresh 2N-slot table per partition):
 //
 //   * table slot = {int64 key, int64 size} (16 B, one 32-B sector holds two) in
 //     HBM/L2; optional per-slot payload {sum, sumsq, min, max} per cont column.
-//   * the insert kernel streams the key column with 256-bit loads and first
-//     folds rows into a per-CTA shared-memory table (4096 slots, ATOMS), so
-//     hot keys (Zipf heads, low-cardinality columns) cost one global atomic
-//     per CTA instead of one per row; misses go straight to the global table
-//     (RED.ADD after a key CAS).
-//   * load factor is kept <= 0.5 BY CONSTRUCTION: before a batch of B rows is
-//     launched the table has capacity >= 2*(U + B) where U is an upper bound on
-//     the distinct keys so far (true count read back asynchronously through a
-//     pinned mailbox, plus rows launched since).  Linear probing therefore
-//     always terminates and no overflow path exists.  Growth = rehash kernel.
+//   * ONE launch per (column, batch).  The insert kernel streams the key column
+//     with 256-bit loads and first folds rows into a per-CTA shared-memory
+//     table (4096 slots, ATOMS), so hot keys (Zipf heads, low-cardinality
+//     columns) cost one global atomic per distinct key per CTA instead of one
+//     per row; a CTA whose first tile shows < 25 % reuse bypasses shared memory
+//     (high-cardinality columns) and goes straight to the global table
+//     (key CAS + RED.ADD on the size).
+//   * the table is sized from a CARDINALITY ESTIMATE (exact distinct count of
+//     the first 2^20 rows, inverted through U = K(1 - exp(-s/K)), or the
+//     caller's hint), not from the worst case.  Correctness never depends on
+//     the estimate: a thread may add at most `budget` new keys per launch
+//     (keeps the load factor <= 0.5) and gives up after 128 probes; a refused
+//     (key, count) pair goes to an overflow ARENA sized for the launch.  The
+//     next call on the handle ("settle") reads the counters back, grows the
+//     table if the arena is non-empty and merges the arena into it.
 //   * the null key (dropna=False) and the one key equal to the EMPTY sentinel
 //     (INT64_MIN) live in two "special" groups outside the table.
 //
-// Throughput bound: shared/L2 atomic units (~1 atomic/clk/SM), not HBM; see
-// DESIGN.md "K3 roofline".
+// Throughput bound: shared/L2 atomic units and random 32-B sector traffic, not
+// the HBM stream; see DESIGN.md "K3 roofline".
 #include <algorithm>
+#include <mutex>
 #include <new>
 
 #include "common.cuh"
@@ -32,8 +39,10 @@ namespace nvtb {
 constexpr int kSmemSlots = 4096;   // per-CTA pre-aggregation table
 constexpr int kSmemProbes = 4;
 constexpr int kInsertSmemBytes = kSmemSlots * (int)(sizeof(long long) + sizeof(unsigned int));
-constexpr int64_t kChunkRows = (int64_t)1 << 23;  // rows per launch
-constexpr int64_t kMinCapacity = 1 << 10;
+constexpr int kMaxProbes = 128;    // global probe limit before a pair is refused
+constexpr int64_t kSampleRows = (int64_t)1 << 20;
+constexpr int64_t kMinCapacity = 1 << 12;
+constexpr int kInsertCtasPerSm = 4;
 
 // min/max are kept as order-preserving int64 images of the double so that the
 // native 64-bit atomicMin/atomicMax can be used.
@@ -64,25 +73,35 @@ struct Table {
   int n_agg;
 };
 
-// counters (device, unsigned long long): 0 = distinct keys in table,
-// special groups: [0] = null key, [1] = INT64_MIN key
-struct Special {
-  unsigned long long n_unique;
-  unsigned long long size[2];
+struct Counters {
+  unsigned long long n_unique;   // distinct keys in the table
+  unsigned long long size[2];    // special groups: [0] null key, [1] INT64_MIN key
+  unsigned long long ovf_count;  // pairs refused into the arena by the pending launch
+};
+
+struct Arena {
+  int64_t* keys;
+  int64_t* sizes;
+  double* vals;      // [cap * 4 * n_agg] or nullptr
+  int64_t cap;
+  int slot;          // index in the shared arena pool, -1 = private allocation
 };
 
 }  // namespace nvtb
 
 struct nvtb_hashagg {
   nvtb::Table t;
-  nvtb::Special* ctr;        // device
+  nvtb::Counters* ctr;       // device
   double* special_vals;      // device [2][4*n_agg]
-  nvtb::Special* mailbox;    // pinned host
-  cudaEvent_t mailbox_ev;
-  bool mailbox_pending;
-  int64_t u_known;           // distinct keys at the last completed readback
-  int64_t rows_since;        // rows launched after that readback was enqueued
-  int64_t rows_at_enqueue;   // rows_since value that the pending readback covers
+  nvtb::Counters* mailbox;   // pinned host
+  cudaEvent_t ev;
+  bool pending;              // a launch whose counters have not been read back
+  nvtb::Arena arena;         // arena of the pending launch
+  cudaStream_t pending_stream;
+  int64_t u_known;           // distinct keys at the last settle
+  int64_t rows_total;        // rows folded in so far
+  double k_est;              // cardinality estimate (0 = none yet)
+  int64_t hint;
   int n_agg;
 };
 
@@ -97,35 +116,62 @@ __device__ __forceinline__ void vals_combine(double* __restrict__ dst,
   if (mx == mx) atomicMax(reinterpret_cast<long long*>(dst + 3), (long long)enc_ordered(mx));
 }
 
-// find-or-claim the slot of `key` (key != kEmptyKey).  Load factor <= 0.5 is
-// guaranteed by the host, so the loop terminates.
-__device__ __forceinline__ int64_t table_find_or_insert(const Table& t,
-                                                        int64_t key,
-                                                        Special* ctr) {
+// find the slot of `key`, claiming an empty one if the thread still has budget
+// for new keys.  Returns -1 when the pair has to be refused (budget exhausted or
+// kMaxProbes slots inspected).  key != kEmptyKey.
+__device__ __forceinline__ int64_t table_upsert(const Table& t, int64_t key,
+                                                int64_t& budget, unsigned& n_new) {
   const int64_t mask = t.capacity - 1;
   int64_t slot = (int64_t)(table_mix64((uint64_t)key) & (uint64_t)mask);
-  while (true) {
+#pragma unroll 1
+  for (int probe = 0; probe < kMaxProbes; ++probe) {
     long long* kp = reinterpret_cast<long long*>(t.slots + 2 * slot);
     long long cur = __ldcg(kp);
     if (cur == key) return slot;
     if (cur == kEmptyKey) {
+      if (budget <= 0) return -1;
       long long prev = (long long)atomicCAS(
           reinterpret_cast<unsigned long long*>(kp),
           (unsigned long long)kEmptyKey, (unsigned long long)key);
       if (prev == kEmptyKey) {
-        atomicAdd(&ctr->n_unique, 1ull);
+        --budget;
+        ++n_new;
         return slot;
       }
       if (prev == key) return slot;
     }
     slot = (slot + 1) & mask;
   }
+  return -1;
 }
 
 __device__ __forceinline__ void table_add_size(const Table& t, int64_t slot,
                                                int64_t add) {
   atomicAdd(reinterpret_cast<unsigned long long*>(t.slots + 2 * slot + 1),
             (unsigned long long)add);
+}
+
+// warp-aggregated append of one refused pair (divergent callers allowed)
+__device__ __forceinline__ int64_t arena_claim(Counters* ctr) {
+  const unsigned active = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(active) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(&ctr->ovf_count, (unsigned long long)__popc(active));
+  base = __shfl_sync(active, base, leader);
+  return (int64_t)base + __popc(active & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void upsert_size(const Table& t, const Arena& a, Counters* ctr,
+                                            int64_t key, int64_t add, int64_t& budget,
+                                            unsigned& n_new) {
+  const int64_t slot = table_upsert(t, key, budget, n_new);
+  if (slot >= 0) {
+    table_add_size(t, slot, add);
+  } else {
+    const int64_t o = arena_claim(ctr);
+    if (o < a.cap) { a.keys[o] = key; a.sizes[o] = add; }
+  }
 }
 
 __global__ void table_init_kernel(Table t) {
@@ -143,9 +189,9 @@ __global__ void table_init_kernel(Table t) {
   }
 }
 
-__global__ void special_init_kernel(Special* ctr, double* special_vals, int n_agg) {
+__global__ void special_init_kernel(Counters* ctr, double* special_vals, int n_agg) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    ctr->n_unique = 0; ctr->size[0] = 0; ctr->size[1] = 0;
+    ctr->n_unique = 0; ctr->size[0] = 0; ctr->size[1] = 0; ctr->ovf_count = 0;
     for (int g = 0; g < 2; ++g)
       for (int j = 0; j < n_agg; ++j) {
         double* v = special_vals + (g * n_agg + j) * 4;
@@ -157,54 +203,98 @@ __global__ void special_init_kernel(Special* ctr, double* special_vals, int n_ag
 }
 
 // ---------------------------------------------------------------------------
-// insert, keys only (Categorify): smem pre-aggregation + global table
+// insert, keys only (Categorify)
 // ---------------------------------------------------------------------------
 template <typename KeyT>
 __global__ void __launch_bounds__(kThreads)
 insert_keys_kernel(const KeyT* __restrict__ keys,
                    const uint8_t* __restrict__ mask, int64_t n, Table t,
-                   Special* ctr) {
+                   Counters* ctr, Arena arena, int64_t thread_budget) {
   // 48 KB of dynamic shared memory: keys[4096] (8 B) then counts[4096] (4 B)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   long long* skeys = reinterpret_cast<long long*>(smem_raw);
   unsigned int* scnt = reinterpret_cast<unsigned int*>(smem_raw + sizeof(long long) * kSmemSlots);
   __shared__ unsigned long long s_null, s_min;
+  __shared__ unsigned int s_hits, s_rows, s_new;
+  __shared__ int s_bypass;
   for (int s = threadIdx.x; s < kSmemSlots; s += kThreads) {
     skeys[s] = kEmptyKey;
     scnt[s] = 0u;
   }
-  if (threadIdx.x == 0) { s_null = 0ull; s_min = 0ull; }
+  if (threadIdx.x == 0) { s_null = 0ull; s_min = 0ull; s_hits = 0u; s_rows = 0u; s_new = 0u; s_bypass = 0; }
   __syncthreads();
 
-  unsigned int n_null = 0, n_min = 0;
+  unsigned int n_null = 0, n_min = 0, n_new = 0;
+  int64_t budget = thread_budget;
+  bool bypass = false;
   const bool aligned = is_aligned32(keys);
-  for_each_row<KeyT>(keys, mask, n, aligned, [&](int64_t, KeyT x, bool valid) {
+
+  auto fold = [&](KeyT x, bool valid, unsigned& hits, unsigned& rows) {
     if (!valid) { n_null++; return; }
     const long long k = (long long)x;
     if (sizeof(KeyT) == 8 && k == kEmptyKey) { n_min++; return; }
-    const uint64_t h = table_mix64((uint64_t)k);
-    // upper hash bits pick the smem slot so that it is independent of the
-    // global slot (low bits)
-    unsigned s = (unsigned)(h >> 40) & (kSmemSlots - 1);
+    rows++;
+    if (!bypass) {
+      const uint64_t h = table_mix64((uint64_t)k);
+      // upper hash bits pick the smem slot, independent of the global slot bits
+      unsigned s = (unsigned)(h >> 40) & (kSmemSlots - 1);
 #pragma unroll
-    for (int p = 0; p < kSmemProbes; ++p) {
-      long long cur = *reinterpret_cast<volatile long long*>(&skeys[s]);
-      if (cur == kEmptyKey) {
-        cur = (long long)atomicCAS(
-            reinterpret_cast<unsigned long long*>(&skeys[s]),
-            (unsigned long long)kEmptyKey, (unsigned long long)k);
-        if (cur == kEmptyKey) cur = k;
+      for (int p = 0; p < kSmemProbes; ++p) {
+        long long cur = *reinterpret_cast<volatile long long*>(&skeys[s]);
+        if (cur == k) {
+          atomicAdd(&scnt[s], 1u);
+          hits++;
+          return;
+        }
+        if (cur == kEmptyKey) {
+          cur = (long long)atomicCAS(reinterpret_cast<unsigned long long*>(&skeys[s]),
+                                     (unsigned long long)kEmptyKey, (unsigned long long)k);
+          if (cur == kEmptyKey || cur == k) {
+            atomicAdd(&scnt[s], 1u);
+            return;
+          }
+        }
+        s = (s + 1) & (kSmemSlots - 1);
       }
-      if (cur == k) {
-        atomicAdd(&scnt[s], 1u);
-        return;
-      }
-      s = (s + 1) & (kSmemSlots - 1);
     }
-    // smem neighbourhood full: straight to the global table
-    const int64_t slot = table_find_or_insert(t, k, ctr);
-    table_add_size(t, slot, 1);
-  });
+    upsert_size(t, arena, ctr, k, 1, budget, n_new);
+  };
+
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  bool first = true;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * kTile;
+    unsigned hits = 0, rows = 0;
+    if (aligned && base + kTile <= n) {
+      KeyT v[kGroups][kRows];
+      unsigned m[kGroups];
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        const int64_t i = base + (int64_t)g * (kThreads * kRows) + (int64_t)threadIdx.x * kRows;
+        ld_rows8<KeyT>(keys + i, v[g]);
+        m[g] = valid8(mask, i);
+      }
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g)
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) fold(v[g][k], (m[g] >> k) & 1u, hits, rows);
+    } else {
+      const int64_t end = (base + kTile < n) ? base + kTile : n;
+      for (int64_t i = base + threadIdx.x; i < end; i += kThreads)
+        fold(keys[i], valid1(mask, i), hits, rows);
+    }
+    if (first) {
+      // after its first tile the CTA decides whether shared-memory folding pays:
+      // < 25 % of the rows met an already-present key  =>  go straight to global
+      first = false;
+      if (hits) atomicAdd(&s_hits, hits);
+      if (rows) atomicAdd(&s_rows, rows);
+      __syncthreads();
+      if (threadIdx.x == 0) s_bypass = (s_hits * 4u < s_rows) ? 1 : 0;
+      __syncthreads();
+      bypass = (s_bypass != 0);
+    }
+  }
 
   if (n_null) atomicAdd(&s_null, (unsigned long long)n_null);
   if (n_min) atomicAdd(&s_min, (unsigned long long)n_min);
@@ -212,14 +302,14 @@ insert_keys_kernel(const KeyT* __restrict__ keys,
   // flush the CTA-local aggregates: one global update per distinct key per CTA
   for (int s = threadIdx.x; s < kSmemSlots; s += kThreads) {
     const long long k = skeys[s];
-    if (k != kEmptyKey) {
-      const int64_t slot = table_find_or_insert(t, k, ctr);
-      table_add_size(t, slot, (int64_t)scnt[s]);
-    }
+    if (k != kEmptyKey) upsert_size(t, arena, ctr, k, (int64_t)scnt[s], budget, n_new);
   }
+  if (n_new) atomicAdd(&s_new, n_new);
+  __syncthreads();
   if (threadIdx.x == 0) {
     if (s_null) atomicAdd(&ctr->size[0], s_null);
     if (s_min) atomicAdd(&ctr->size[1], s_min);
+    if (s_new) atomicAdd(&ctr->n_unique, (unsigned long long)s_new);
   }
 }
 
@@ -253,13 +343,17 @@ template <typename KeyT>
 __global__ void __launch_bounds__(kThreads)
 insert_agg_kernel(const KeyT* __restrict__ keys,
                   const uint8_t* __restrict__ mask, AggCols agg, int64_t n,
-                  Table t, Special* ctr, double* special_vals) {
+                  Table t, Counters* ctr, double* special_vals, Arena arena,
+                  int64_t thread_budget) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t budget = thread_budget;
+  unsigned n_new = 0;
+  const double nan = __longlong_as_double(0x7FF8000000000000ll);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += stride) {
     const bool valid = valid1(mask, i);
     const long long k = valid ? (long long)keys[i] : 0;
-    double* vdst;
+    double* vdst = nullptr;
     if (!valid) {
       atomicAdd(&ctr->size[0], 1ull);
       vdst = special_vals;
@@ -267,23 +361,41 @@ insert_agg_kernel(const KeyT* __restrict__ keys,
       atomicAdd(&ctr->size[1], 1ull);
       vdst = special_vals + (int64_t)t.n_agg * 4;
     } else {
-      const int64_t slot = table_find_or_insert(t, k, ctr);
-      table_add_size(t, slot, 1);
-      vdst = t.vals + slot * t.n_agg * 4;
+      const int64_t slot = table_upsert(t, k, budget, n_new);
+      if (slot >= 0) {
+        table_add_size(t, slot, 1);
+        vdst = t.vals + slot * t.n_agg * 4;
+      } else {
+        const int64_t o = arena_claim(ctr);
+        if (o < arena.cap) {
+          arena.keys[o] = k;
+          arena.sizes[o] = 1;
+          for (int j = 0; j < t.n_agg; ++j) {
+            double v;
+            double* w = arena.vals + (o * t.n_agg + j) * 4;
+            if (load_agg(agg, j, i, &v)) { w[0] = v; w[1] = v * v; w[2] = v; w[3] = v; }
+            else { w[0] = 0.0; w[1] = 0.0; w[2] = nan; w[3] = nan; }
+          }
+        }
+        continue;
+      }
     }
     for (int j = 0; j < t.n_agg; ++j) {
       double v;
       if (load_agg(agg, j, i, &v)) vals_combine(vdst + j * 4, v, v * v, v, v);
     }
   }
+  if (n_new) atomicAdd(&ctr->n_unique, (unsigned long long)n_new);
 }
 
-// merge pre-aggregated rows (other GPUs' partials, or an old table on growth)
+// merge pre-aggregated rows (other GPUs' partials, or a drained arena)
 __global__ void __launch_bounds__(kThreads)
 merge_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes,
-             const double* __restrict__ vals, int64_t n, Table t, Special* ctr,
-             double* special_vals) {
+             const double* __restrict__ vals, int64_t n, Table t, Counters* ctr,
+             double* special_vals, Arena arena, int64_t thread_budget) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t budget = thread_budget;
+  unsigned n_new = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += stride) {
     const long long k = keys[i];
@@ -292,7 +404,18 @@ merge_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes
       atomicAdd(&ctr->size[1], (unsigned long long)sizes[i]);
       vdst = special_vals + (int64_t)t.n_agg * 4;
     } else {
-      const int64_t slot = table_find_or_insert(t, k, ctr);
+      const int64_t slot = table_upsert(t, k, budget, n_new);
+      if (slot < 0) {
+        const int64_t o = arena_claim(ctr);
+        if (o < arena.cap) {
+          arena.keys[o] = k;
+          arena.sizes[o] = sizes[i];
+          if (vals != nullptr)
+            for (int j = 0; j < t.n_agg * 4; ++j)
+              arena.vals[o * t.n_agg * 4 + j] = vals[i * t.n_agg * 4 + j];
+        }
+        continue;
+      }
       table_add_size(t, slot, sizes[i]);
       vdst = t.vals + slot * t.n_agg * 4;
     }
@@ -302,18 +425,27 @@ merge_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes
         vals_combine(vdst + j * 4, v[0], v[1], v[2], v[3]);
       }
   }
+  if (n_new) atomicAdd(&ctr->n_unique, (unsigned long long)n_new);
 }
 
-// rehash an old table into a new one (keys are distinct: plain stores after
-// the claim; n_unique is carried over by the host)
+// rehash an old table into a new, larger one (keys are distinct: plain stores
+// after the claim; n_unique is unchanged)
 __global__ void __launch_bounds__(kThreads)
-rehash_kernel(Table old_t, Table new_t, Special* scratch_ctr) {
+rehash_kernel(Table old_t, Table new_t) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t mask = new_t.capacity - 1;
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
        s < old_t.capacity; s += stride) {
     const long long k = old_t.slots[2 * s];
     if (k == kEmptyKey) continue;
-    const int64_t slot = table_find_or_insert(new_t, k, scratch_ctr);
+    int64_t slot = (int64_t)(table_mix64((uint64_t)k) & (uint64_t)mask);
+    while (true) {  // the new table is at most half full: terminates
+      long long prev = (long long)atomicCAS(
+          reinterpret_cast<unsigned long long*>(new_t.slots + 2 * slot),
+          (unsigned long long)kEmptyKey, (unsigned long long)k);
+      if (prev == kEmptyKey) break;
+      slot = (slot + 1) & mask;
+    }
     new_t.slots[2 * slot + 1] = old_t.slots[2 * s + 1];
     for (int j = 0; j < old_t.n_agg * 4; ++j)
       new_t.vals[slot * old_t.n_agg * 4 + j] = old_t.vals[s * old_t.n_agg * 4 + j];
@@ -327,7 +459,7 @@ export_kernel(Table t, int64_t* __restrict__ keys_out,
               unsigned long long* cursor) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
-  // capacity is a power of two >= 1024, so every warp runs the same trip count
+  // capacity is a power of two >= 4096, so every warp runs the same trip count
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
        s < t.capacity; s += stride) {
     const long long k = t.slots[2 * s];
@@ -440,6 +572,13 @@ pack_keys2_kernel(const int32_t* __restrict__ a, const uint8_t* __restrict__ ma,
   }
 }
 
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int plain_grid(int64_t n) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
+}
+
 static int table_alloc(Table* t, int64_t capacity, int n_agg, cudaStream_t st) {
   t->capacity = capacity;
   t->n_agg = n_agg;
@@ -448,9 +587,7 @@ static int table_alloc(Table* t, int64_t capacity, int n_agg, cudaStream_t st) {
   NVTB_CUDA_OK(cudaMallocAsync(&t->slots, sizeof(int64_t) * 2 * capacity, st));
   if (n_agg > 0)
     NVTB_CUDA_OK(cudaMallocAsync(&t->vals, sizeof(double) * 4 * n_agg * capacity, st));
-  int grid = (int)std::min<int64_t>((capacity + kThreads - 1) / kThreads,
-                                    (int64_t)sm_count() * 8);
-  table_init_kernel<<<grid, kThreads, 0, st>>>(*t);
+  table_init_kernel<<<plain_grid(capacity), kThreads, 0, st>>>(*t);
   NVTB_LAUNCH_OK();
   return NVTB_OK;
 }
@@ -468,65 +605,209 @@ static int64_t next_pow2(int64_t v) {
   return p;
 }
 
-// poll / wait the asynchronous distinct-count readback
-static int mailbox_poll(nvtb_hashagg* h, bool block) {
-  if (!h->mailbox_pending) return NVTB_OK;
-  cudaError_t e = block ? cudaEventSynchronize(h->mailbox_ev)
-                        : cudaEventQuery(h->mailbox_ev);
-  if (e == cudaErrorNotReady) return NVTB_OK;
-  if (e != cudaSuccess) {
-    set_error("mailbox event failed: %s", cudaGetErrorString(e));
-    return NVTB_ECUDA;
-  }
-  h->u_known = (int64_t)h->mailbox->n_unique;
-  h->rows_since -= h->rows_at_enqueue;
-  h->mailbox_pending = false;
+static int settle(nvtb_hashagg* h);
+
+static int arena_alloc(Arena* a, int64_t cap, int n_agg, cudaStream_t st) {
+  a->cap = cap; a->keys = nullptr; a->sizes = nullptr; a->vals = nullptr; a->slot = -1;
+  if (cap <= 0) return NVTB_OK;
+  NVTB_CUDA_OK(cudaMallocAsync(&a->keys, sizeof(int64_t) * cap, st));
+  NVTB_CUDA_OK(cudaMallocAsync(&a->sizes, sizeof(int64_t) * cap, st));
+  if (n_agg > 0) NVTB_CUDA_OK(cudaMallocAsync(&a->vals, sizeof(double) * 4 * n_agg * cap, st));
   return NVTB_OK;
 }
 
-static int mailbox_post(nvtb_hashagg* h, cudaStream_t st) {
-  if (h->mailbox_pending) return NVTB_OK;  // one readback in flight at a time
-  NVTB_CUDA_OK(cudaMemcpyAsync(h->mailbox, h->ctr, sizeof(Special),
-                               cudaMemcpyDeviceToHost, st));
-  NVTB_CUDA_OK(cudaEventRecord(h->mailbox_ev, st));
-  h->mailbox_pending = true;
-  h->rows_at_enqueue = h->rows_since;
+// The arena of a launch must be able to hold one pair per input row, but is
+// almost never touched.  Two pooled arenas (double buffering) serve every
+// handle: acquiring a slot that still belongs to an unsettled launch settles
+// that launch first, so at most two arenas exist however many columns are fitted.
+struct ArenaSlot {
+  int64_t* keys; int64_t* sizes; double* vals;
+  int64_t cap_alloc; int64_t vals_alloc;
+  nvtb_hashagg* owner;
+  uint64_t stamp;
+};
+static ArenaSlot g_slots[2] = {};
+static uint64_t g_stamp = 0;
+static std::recursive_mutex g_arena_mu;
+
+static int arena_acquire(nvtb_hashagg* h, Arena* out, int64_t cap, int n_agg) {
+  std::lock_guard<std::recursive_mutex> lk(g_arena_mu);
+  int pick = -1;
+  for (int i = 0; i < 2; ++i)
+    if (g_slots[i].owner == nullptr) { pick = i; break; }
+  if (pick < 0) {
+    pick = g_slots[0].stamp < g_slots[1].stamp ? 0 : 1;
+    int rc = settle(g_slots[pick].owner);   // releases the slot
+    if (rc) return rc;
+  }
+  ArenaSlot& sl = g_slots[pick];
+  const int64_t need_vals = cap * 4 * n_agg;
+  if (sl.cap_alloc < cap) {
+    NVTB_CUDA_OK(cudaDeviceSynchronize());
+    if (sl.keys) cudaFree(sl.keys);
+    if (sl.sizes) cudaFree(sl.sizes);
+    sl.keys = nullptr; sl.sizes = nullptr; sl.cap_alloc = 0;
+    NVTB_CUDA_OK(cudaMalloc(&sl.keys, sizeof(int64_t) * cap));
+    NVTB_CUDA_OK(cudaMalloc(&sl.sizes, sizeof(int64_t) * cap));
+    sl.cap_alloc = cap;
+  }
+  if (sl.vals_alloc < need_vals) {
+    NVTB_CUDA_OK(cudaDeviceSynchronize());
+    if (sl.vals) cudaFree(sl.vals);
+    sl.vals = nullptr; sl.vals_alloc = 0;
+    NVTB_CUDA_OK(cudaMalloc(&sl.vals, sizeof(double) * need_vals));
+    sl.vals_alloc = need_vals;
+  }
+  sl.owner = h;
+  sl.stamp = ++g_stamp;
+  out->keys = sl.keys; out->sizes = sl.sizes; out->vals = n_agg > 0 ? sl.vals : nullptr;
+  out->cap = cap; out->slot = pick;
   return NVTB_OK;
 }
 
-// make sure the table can take `batch` more rows with load factor <= 0.5
-static int ensure_capacity(nvtb_hashagg* h, int64_t batch, cudaStream_t st) {
-  int rc = mailbox_poll(h, false);
-  if (rc) return rc;
-  int64_t need = 2 * (h->u_known + h->rows_since + batch);
-  if (need <= h->t.capacity) return NVTB_OK;
-  // the bound is stale: get the true distinct count before paying for growth
-  if (!h->mailbox_pending) { rc = mailbox_post(h, st); if (rc) return rc; }
-  rc = mailbox_poll(h, true);
-  if (rc) return rc;
-  if (h->rows_since > 0) {  // rows were launched after that readback: redo it
-    rc = mailbox_post(h, st); if (rc) return rc;
-    rc = mailbox_poll(h, true); if (rc) return rc;
+static int arena_free(Arena* a, cudaStream_t st) {
+  if (a->slot >= 0) {
+    std::lock_guard<std::recursive_mutex> lk(g_arena_mu);
+    g_slots[a->slot].owner = nullptr;
+  } else {
+    if (a->keys) NVTB_CUDA_OK(cudaFreeAsync(a->keys, st));
+    if (a->sizes) NVTB_CUDA_OK(cudaFreeAsync(a->sizes, st));
+    if (a->vals) NVTB_CUDA_OK(cudaFreeAsync(a->vals, st));
   }
-  need = 2 * (h->u_known + h->rows_since + batch);
-  if (need <= h->t.capacity) return NVTB_OK;
-  // grow: 4x headroom over what is known to be needed
-  const int64_t new_cap = next_pow2(std::max<int64_t>(need, 4 * (h->u_known + batch)));
+  a->keys = nullptr; a->sizes = nullptr; a->vals = nullptr; a->cap = 0; a->slot = -1;
+  return NVTB_OK;
+}
+
+// distinct keys expected among `rows` uniform draws from K values
+static double expected_unique(double K, double rows) {
+  if (K <= 0) return 0;
+  return K * -std::expm1(-rows / K);
+}
+
+// invert U = K (1 - exp(-s/K)) for K (bisection); U >= 0.98 s  =>  "all distinct"
+static double estimate_cardinality(double U, double s) {
+  if (U <= 0) return 1.0;
+  if (U >= 0.98 * s) return 1e18;
+  double lo = U, hi = 1e18;
+  for (int it = 0; it < 200; ++it) {
+    const double mid = std::sqrt(lo * hi);
+    if (expected_unique(mid, s) < U) lo = mid; else hi = mid;
+    if (hi / lo < 1.0 + 1e-9) break;
+  }
+  return lo;
+}
+
+static int grow_to(nvtb_hashagg* h, int64_t new_cap, cudaStream_t st) {
+  if (new_cap <= h->t.capacity) return NVTB_OK;
   Table nt;
-  rc = table_alloc(&nt, new_cap, h->n_agg, st);
+  int rc = table_alloc(&nt, new_cap, h->n_agg, st);
   if (rc) return rc;
-  Special* scratch = nullptr;
-  NVTB_CUDA_OK(cudaMallocAsync(&scratch, sizeof(Special), st));
-  NVTB_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(Special), st));
-  int grid = (int)std::min<int64_t>((h->t.capacity + kThreads - 1) / kThreads,
-                                    (int64_t)sm_count() * 8);
-  rehash_kernel<<<grid, kThreads, 0, st>>>(h->t, nt, scratch);
-  NVTB_LAUNCH_OK();
-  NVTB_CUDA_OK(cudaFreeAsync(scratch, st));
+  if (h->u_known > 0 || h->rows_total > 0) {
+    rehash_kernel<<<plain_grid(h->t.capacity), kThreads, 0, st>>>(h->t, nt);
+    NVTB_LAUNCH_OK();
+  }
   rc = table_free(&h->t, st);
   if (rc) return rc;
   h->t = nt;
   return NVTB_OK;
+}
+
+static int launch_merge(nvtb_hashagg* h, const int64_t* keys, const int64_t* sizes,
+                        const double* vals, int64_t n, const Arena& arena, cudaStream_t st) {
+  const int grid = plain_grid(n);
+  const int64_t room = h->t.capacity / 2 - h->u_known;
+  const int64_t budget = std::max<int64_t>(0, room) / ((int64_t)grid * kThreads);
+  merge_kernel<<<grid, kThreads, 0, st>>>(keys, sizes, vals, n, h->t, h->ctr, h->special_vals,
+                                         arena, budget);
+  NVTB_LAUNCH_OK();
+  return NVTB_OK;
+}
+
+// wait for the pending launch, read its counters, and fold a non-empty arena
+// back in after growing the table.  Leaves no pending state.
+static int settle(nvtb_hashagg* h) {
+  if (h == nullptr) return NVTB_OK;
+  while (h->pending) {
+    cudaStream_t st = h->pending_stream;
+    NVTB_CUDA_OK(cudaEventSynchronize(h->ev));
+    h->pending = false;
+    const Counters c = *h->mailbox;
+    h->u_known = (int64_t)c.n_unique;
+    const int64_t ovf = (int64_t)std::min<unsigned long long>(c.ovf_count, (unsigned long long)h->arena.cap);
+    Arena old = h->arena;
+    h->arena = Arena{nullptr, nullptr, nullptr, 0, -1};
+    if (ovf > 0) {
+      // every refused pair may be a new key: size for all of them at load <= 0.25
+      int rc = grow_to(h, next_pow2(4 * (h->u_known + ovf)), st);
+      if (rc) return rc;
+      NVTB_CUDA_OK(cudaMemsetAsync(&h->ctr->ovf_count, 0, sizeof(unsigned long long), st));
+      // budget: capacity/2 - u_known >= ovf, spread over the launch's threads; a pair the
+      // per-thread budget still refuses lands in a fresh arena and is settled by the loop
+      rc = arena_alloc(&h->arena, ovf, h->n_agg, st);
+      if (rc) return rc;
+      rc = launch_merge(h, old.keys, old.sizes, old.vals, ovf, h->arena, st);
+      if (rc) return rc;
+      NVTB_CUDA_OK(cudaMemcpyAsync(h->mailbox, h->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+      NVTB_CUDA_OK(cudaEventRecord(h->ev, st));
+      h->pending = true;
+      h->pending_stream = st;
+    }
+    int rc = arena_free(&old, st);
+    if (rc) return rc;
+  }
+  if (h->rows_total > 0)
+    h->k_est = estimate_cardinality((double)std::max<int64_t>(h->u_known, 1), (double)h->rows_total);
+  return NVTB_OK;
+}
+
+// after a launch: async readback of the counters
+static int post(nvtb_hashagg* h, cudaStream_t st) {
+  NVTB_CUDA_OK(cudaMemcpyAsync(h->mailbox, h->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  NVTB_CUDA_OK(cudaEventRecord(h->ev, st));
+  h->pending = true;
+  h->pending_stream = st;
+  return NVTB_OK;
+}
+
+// size the table for `rows` more rows: load <= 0.5 for the ESTIMATED distinct count
+static int prepare(nvtb_hashagg* h, int64_t rows, cudaStream_t st) {
+  double predicted;
+  if (h->hint > 0) {
+    predicted = (double)std::max<int64_t>(h->hint, h->u_known);
+  } else if (h->k_est > 0) {
+    predicted = expected_unique(h->k_est, (double)(h->rows_total + rows));
+    predicted = std::max(predicted, (double)h->u_known);
+  } else {
+    predicted = (double)h->u_known + (double)rows;   // no information: worst case
+  }
+  predicted = std::min(predicted, (double)h->u_known + (double)rows);
+  const int64_t want = next_pow2((int64_t)(2.5 * predicted) + 1);
+  return grow_to(h, want, st);
+}
+
+template <typename KeyT>
+static int launch_insert(nvtb_hashagg* h, const KeyT* kp, const uint8_t* mp, const AggCols& ac,
+                         int64_t m, cudaStream_t st) {
+  int rc = arena_acquire(h, &h->arena, m, h->n_agg);
+  if (rc) return rc;
+  NVTB_CUDA_OK(cudaMemsetAsync(&h->ctr->ovf_count, 0, sizeof(unsigned long long), st));
+  const int64_t room = std::max<int64_t>(0, h->t.capacity / 2 - h->u_known);
+  if (h->n_agg == 0) {
+    const int grid = scan_grid(m, kInsertCtasPerSm);
+    const int64_t budget = room / ((int64_t)grid * kThreads);
+    NVTB_CUDA_OK(cudaFuncSetAttribute(insert_keys_kernel<KeyT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kInsertSmemBytes));
+    insert_keys_kernel<KeyT><<<grid, kThreads, kInsertSmemBytes, st>>>(kp, mp, m, h->t, h->ctr,
+                                                                        h->arena, budget);
+  } else {
+    const int grid = plain_grid(m);
+    const int64_t budget = room / ((int64_t)grid * kThreads);
+    insert_agg_kernel<KeyT><<<grid, kThreads, 0, st>>>(kp, mp, ac, m, h->t, h->ctr,
+                                                       h->special_vals, h->arena, budget);
+  }
+  NVTB_LAUNCH_OK();
+  h->rows_total += m;
+  return post(h, st);
 }
 
 }  // namespace nvtb
@@ -542,29 +823,48 @@ int nvtb_hashagg_create(nvtb_hashagg_t** out, int n_agg, int64_t capacity_hint) 
   NVTB_REQUIRE(h != nullptr, "host allocation failed");
   memset(h, 0, sizeof(*h));
   h->n_agg = n_agg;
+  h->hint = capacity_hint > 0 ? capacity_hint : 0;
   cudaStream_t st = 0;
-  int rc = table_alloc(&h->t, next_pow2(std::max<int64_t>(2 * capacity_hint, kMinCapacity)), n_agg, st);
+  int rc = table_alloc(&h->t, next_pow2(std::max<int64_t>((int64_t)(2.5 * capacity_hint), kMinCapacity)), n_agg, st);
   if (rc) { delete h; return rc; }
-  NVTB_CUDA_OK(cudaMalloc(&h->ctr, sizeof(Special)));
+  NVTB_CUDA_OK(cudaMalloc(&h->ctr, sizeof(Counters)));
   NVTB_CUDA_OK(cudaMalloc(&h->special_vals, sizeof(double) * 8 * (n_agg > 0 ? n_agg : 1)));
   special_init_kernel<<<1, 32, 0, st>>>(h->ctr, h->special_vals, n_agg);
   NVTB_LAUNCH_OK();
-  NVTB_CUDA_OK(cudaMallocHost(&h->mailbox, sizeof(Special)));
-  NVTB_CUDA_OK(cudaEventCreateWithFlags(&h->mailbox_ev, cudaEventDisableTiming));
+  NVTB_CUDA_OK(cudaMallocHost(&h->mailbox, sizeof(Counters)));
+  NVTB_CUDA_OK(cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming));
   NVTB_CUDA_OK(cudaStreamSynchronize(st));
   *out = h;
   return NVTB_OK;
 }
 
+int nvtb_hashagg_reset(nvtb_hashagg_t* h, void* stream) {
+  NVTB_REQUIRE(h != nullptr, "NULL handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = settle(h);
+  if (rc) return rc;
+  // the table keeps its capacity (and the estimate its value): a second fit over
+  // similar data needs no growth and no sampling pass
+  h->hint = std::max<int64_t>(h->hint, h->u_known);
+  table_init_kernel<<<plain_grid(h->t.capacity), kThreads, 0, st>>>(h->t);
+  NVTB_LAUNCH_OK();
+  special_init_kernel<<<1, 32, 0, st>>>(h->ctr, h->special_vals, h->n_agg);
+  NVTB_LAUNCH_OK();
+  h->u_known = 0;
+  h->rows_total = 0;
+  return NVTB_OK;
+}
+
 int nvtb_hashagg_destroy(nvtb_hashagg_t* h) {
   if (h == nullptr) return NVTB_OK;
+  settle(h);              // hands a pooled arena back
   cudaDeviceSynchronize();
   if (h->t.slots) cudaFree(h->t.slots);
   if (h->t.vals) cudaFree(h->t.vals);
   if (h->ctr) cudaFree(h->ctr);
   if (h->special_vals) cudaFree(h->special_vals);
   if (h->mailbox) cudaFreeHost(h->mailbox);
-  if (h->mailbox_ev) cudaEventDestroy(h->mailbox_ev);
+  if (h->ev) cudaEventDestroy(h->ev);
   delete h;
   return NVTB_OK;
 }
@@ -587,37 +887,27 @@ int nvtb_hashagg_insert(nvtb_hashagg_t* h, const nvtb_col_t* key,
     ac.data[j] = agg_cols[j].data; ac.mask[j] = agg_cols[j].validity; ac.dtype[j] = agg_cols[j].dtype;
   }
   const size_t ksz = dtype_size(key->dtype);
-  for (int64_t off = 0; off < n; off += kChunkRows) {
-    const int64_t m = std::min<int64_t>(kChunkRows, n - off);
-    int rc = ensure_capacity(h, m, st);
+  // batches: [sample of 2^20 rows when nothing is known about the cardinality] + the rest
+  int64_t off = 0;
+  while (off < n) {
+    int rc = settle(h);
+    if (rc) return rc;
+    int64_t m = n - off;
+    const bool blind = (h->hint == 0 && h->k_est == 0);
+    if (blind && m > 4 * kSampleRows) m = kSampleRows;
+    rc = prepare(h, m, st);
     if (rc) return rc;
     const void* kp = (const char*)key->data + off * ksz;
     const uint8_t* mp = key->validity ? key->validity + (off >> 3) : nullptr;  // off % 8 == 0
-    if (h->n_agg == 0) {
-      const int grid = scan_grid(m, 4);
-      if (key->dtype == NVTB_I32) {
-        NVTB_CUDA_OK(cudaFuncSetAttribute(insert_keys_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kInsertSmemBytes));
-        insert_keys_kernel<int32_t><<<grid, kThreads, kInsertSmemBytes, st>>>((const int32_t*)kp, mp, m, h->t, h->ctr);
-      } else {
-        NVTB_CUDA_OK(cudaFuncSetAttribute(insert_keys_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kInsertSmemBytes));
-        insert_keys_kernel<int64_t><<<grid, kThreads, kInsertSmemBytes, st>>>((const int64_t*)kp, mp, m, h->t, h->ctr);
-      }
-    } else {
-      AggCols a2 = ac;
-      for (int j = 0; j < h->n_agg; ++j) {
-        a2.data[j] = (const char*)ac.data[j] + off * dtype_size(ac.dtype[j]);
-        a2.mask[j] = ac.mask[j] ? ac.mask[j] + (off >> 3) : nullptr;
-      }
-      const int grid = (int)std::min<int64_t>((m + kThreads - 1) / kThreads, (int64_t)sm_count() * 8);
-      if (key->dtype == NVTB_I32)
-        insert_agg_kernel<int32_t><<<grid, kThreads, 0, st>>>((const int32_t*)kp, mp, a2, m, h->t, h->ctr, h->special_vals);
-      else
-        insert_agg_kernel<int64_t><<<grid, kThreads, 0, st>>>((const int64_t*)kp, mp, a2, m, h->t, h->ctr, h->special_vals);
+    AggCols a2 = ac;
+    for (int j = 0; j < h->n_agg; ++j) {
+      a2.data[j] = (const char*)ac.data[j] + off * dtype_size(ac.dtype[j]);
+      a2.mask[j] = ac.mask[j] ? ac.mask[j] + (off >> 3) : nullptr;
     }
-    NVTB_LAUNCH_OK();
-    h->rows_since += m;
-    rc = mailbox_post(h, st);
+    if (key->dtype == NVTB_I32) rc = launch_insert<int32_t>(h, (const int32_t*)kp, mp, a2, m, st);
+    else                        rc = launch_insert<int64_t>(h, (const int64_t*)kp, mp, a2, m, st);
     if (rc) return rc;
+    off += m;
   }
   return NVTB_OK;
 }
@@ -630,26 +920,26 @@ int nvtb_hashagg_merge(nvtb_hashagg_t* h, const int64_t* keys,
   NVTB_REQUIRE(keys != nullptr && sizes != nullptr, "NULL keys/sizes");
   NVTB_REQUIRE(h->n_agg == 0 || vals != nullptr, "vals is NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  for (int64_t off = 0; off < n; off += kChunkRows) {
-    const int64_t m = std::min<int64_t>(kChunkRows, n - off);
-    int rc = ensure_capacity(h, m, st);
-    if (rc) return rc;
-    const int grid = (int)std::min<int64_t>((m + kThreads - 1) / kThreads, (int64_t)sm_count() * 8);
-    merge_kernel<<<grid, kThreads, 0, st>>>(keys + off, sizes + off,
-                                           vals ? vals + off * h->n_agg * 4 : nullptr,
-                                           m, h->t, h->ctr, h->special_vals);
-    NVTB_LAUNCH_OK();
-    h->rows_since += m;
-    rc = mailbox_post(h, st);
-    if (rc) return rc;
-  }
-  return NVTB_OK;
+  int rc = settle(h);
+  if (rc) return rc;
+  // pre-aggregated rows: distinct keys within the batch => every row may be new
+  rc = grow_to(h, next_pow2((int64_t)(2.5 * (double)(h->u_known + n)) + 1), st);
+  if (rc) return rc;
+  rc = arena_acquire(h, &h->arena, n, h->n_agg);
+  if (rc) return rc;
+  NVTB_CUDA_OK(cudaMemsetAsync(&h->ctr->ovf_count, 0, sizeof(unsigned long long), st));
+  rc = launch_merge(h, keys, sizes, vals, n, h->arena, st);
+  if (rc) return rc;
+  h->rows_total += n;
+  return post(h, st);
 }
 
 int nvtb_hashagg_add_null_group(nvtb_hashagg_t* h, int64_t size, const double* vals_host) {
   NVTB_REQUIRE(h != nullptr && size >= 0, "NULL handle or size < 0");
   // tiny, synchronous: used once per rank in the cross-GPU merge
-  Special s;
+  int rc = settle(h);
+  if (rc) return rc;
+  Counters s;
   NVTB_CUDA_OK(cudaDeviceSynchronize());
   NVTB_CUDA_OK(cudaMemcpy(&s, h->ctr, sizeof(s), cudaMemcpyDeviceToHost));
   s.size[0] += (unsigned long long)size;
@@ -677,14 +967,12 @@ int nvtb_hashagg_add_null_group(nvtb_hashagg_t* h, int64_t size, const double* v
 int nvtb_hashagg_size(nvtb_hashagg_t* h, int64_t* n_unique, int64_t* null_size, void* stream) {
   NVTB_REQUIRE(h != nullptr, "NULL handle");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = mailbox_poll(h, true);
+  int rc = settle(h);
   if (rc) return rc;
-  Special s;
-  NVTB_CUDA_OK(cudaMemcpyAsync(h->mailbox, h->ctr, sizeof(Special), cudaMemcpyDeviceToHost, st));
+  NVTB_CUDA_OK(cudaMemcpyAsync(h->mailbox, h->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   NVTB_CUDA_OK(cudaStreamSynchronize(st));
-  s = *h->mailbox;
+  const Counters s = *h->mailbox;
   h->u_known = (int64_t)s.n_unique;
-  h->rows_since = 0;
   if (n_unique) *n_unique = (int64_t)s.n_unique + (s.size[1] ? 1 : 0);
   if (null_size) *null_size = (int64_t)s.size[0];
   return NVTB_OK;
@@ -697,7 +985,7 @@ int nvtb_hashagg_export(nvtb_hashagg_t* h, int64_t* keys_out, int64_t* sizes_out
   int64_t nu = 0, ns = 0;
   int rc = nvtb_hashagg_size(h, &nu, &ns, stream);
   if (rc) return rc;
-  const Special s = *h->mailbox;
+  const Counters s = *h->mailbox;
   double dec[8 * kMaxAgg];
   if (h->n_agg > 0) {
     double* d_dec = nullptr;
@@ -715,8 +1003,7 @@ int nvtb_hashagg_export(nvtb_hashagg_t* h, int64_t* keys_out, int64_t* sizes_out
   unsigned long long* cursor = nullptr;
   NVTB_CUDA_OK(cudaMallocAsync(&cursor, sizeof(unsigned long long), st));
   NVTB_CUDA_OK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
-  int grid = (int)std::min<int64_t>((h->t.capacity + kThreads - 1) / kThreads, (int64_t)sm_count() * 8);
-  export_kernel<<<grid, kThreads, 0, st>>>(h->t, keys_out, sizes_out, vals_out, cursor);
+  export_kernel<<<plain_grid(h->t.capacity), kThreads, 0, st>>>(h->t, keys_out, sizes_out, vals_out, cursor);
   NVTB_LAUNCH_OK();
   NVTB_CUDA_OK(cudaFreeAsync(cursor, st));
   if (s.size[1]) {  // the INT64_MIN key lives outside the table: append it last
@@ -743,7 +1030,7 @@ int nvtb_partition_by_owner(const int64_t* keys, int64_t n, int n_parts,
   unsigned long long* d = nullptr;
   NVTB_CUDA_OK(cudaMallocAsync(&d, sizeof(unsigned long long) * 128, st));
   NVTB_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * 128, st));
-  const int grid = (int)std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8);
+  const int grid = plain_grid(n);
   owner_count_kernel<<<grid, kThreads, 0, st>>>(keys, n, n_parts, d);
   NVTB_LAUNCH_OK();
   unsigned long long hc[64];
@@ -763,8 +1050,7 @@ int nvtb_gather_i64(const int64_t* src, const int64_t* perm, int64_t n, int64_t*
   NVTB_REQUIRE(n >= 0, "n < 0");
   if (n == 0) return NVTB_OK;
   NVTB_REQUIRE(src && perm && dst, "NULL pointer");
-  const int grid = (int)std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8);
-  gather_i64_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(src, perm, n, dst);
+  gather_i64_kernel<<<plain_grid(n), kThreads, 0, (cudaStream_t)stream>>>(src, perm, n, dst);
   NVTB_LAUNCH_OK();
   return NVTB_OK;
 }
@@ -774,9 +1060,7 @@ int nvtb_gather_f64_rows(const double* src, const int64_t* perm, int64_t n, int 
   NVTB_REQUIRE(n >= 0 && row_width >= 1, "bad n/row_width");
   if (n == 0) return NVTB_OK;
   NVTB_REQUIRE(src && perm && dst, "NULL pointer");
-  const int64_t total = n * row_width;
-  const int grid = (int)std::min<int64_t>((total + kThreads - 1) / kThreads, (int64_t)sm_count() * 8);
-  gather_f64_rows_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(src, perm, n, row_width, dst);
+  gather_f64_rows_kernel<<<plain_grid(n * row_width), kThreads, 0, (cudaStream_t)stream>>>(src, perm, n, row_width, dst);
   NVTB_LAUNCH_OK();
   return NVTB_OK;
 }
@@ -787,9 +1071,7 @@ int nvtb_pack_keys2(const nvtb_col_t* a, const nvtb_col_t* b, int64_t n,
   NVTB_REQUIRE(a->dtype == NVTB_I32 && b->dtype == NVTB_I32, "pack_keys2 needs int32 columns");
   if (n == 0) return NVTB_OK;
   NVTB_REQUIRE(a->data && b->data && keys_out, "NULL data");
-  const int64_t n8 = (n + 7) / 8;
-  const int grid = (int)std::min<int64_t>((n8 + kThreads - 1) / kThreads, (int64_t)sm_count() * 8);
-  pack_keys2_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+  pack_keys2_kernel<<<plain_grid((n + 7) / 8), kThreads, 0, (cudaStream_t)stream>>>(
       (const int32_t*)a->data, a->validity, (const int32_t*)b->data, b->validity, n, keys_out, validity_out);
   NVTB_LAUNCH_OK();
   return NVTB_OK;

@@ -185,7 +185,7 @@ static int lookup_create(Lookup* t, const int64_t* keys, int64_t n, bool may_hav
   t->capacity = pow2_at_least(2 * n);
   t->min_key_pos = -1;
   t->slots = nullptr;
-  NVTB_CUDA_OK(cudaMalloc(&t->slots, sizeof(int64_t) * 2 * t->capacity));
+  NVTB_CUDA_OK(cudaMallocAsync(&t->slots, sizeof(int64_t) * 2 * t->capacity, st));
   const int g0 = (int)std::min<int64_t>((t->capacity + kThreads - 1) / kThreads, (int64_t)sm_count() * 8);
   lookup_init_kernel<<<g0, kThreads, 0, st>>>(t->slots, t->capacity);
   NVTB_LAUNCH_OK();
@@ -297,8 +297,8 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* siz
     NVTB_CUDA_OK(cudaFreeAsync(tmp, st));
 
     if (n_keep > 0) {
-      NVTB_CUDA_OK(cudaMalloc(&v->keys, sizeof(int64_t) * n_keep));
-      NVTB_CUDA_OK(cudaMalloc(&v->sizes, sizeof(int64_t) * n_keep));
+      NVTB_CUDA_OK(cudaMallocAsync(&v->keys, sizeof(int64_t) * n_keep, st));
+      NVTB_CUDA_OK(cudaMallocAsync(&v->sizes, sizeof(int64_t) * n_keep, st));
       NVTB_CUDA_OK(cudaMemcpyAsync(v->keys, k2, sizeof(int64_t) * n_keep, cudaMemcpyDeviceToDevice, st));
       NVTB_CUDA_OK(cudaMemcpyAsync(v->sizes, s2, sizeof(int64_t) * n_keep, cudaMemcpyDeviceToDevice, st));
     }
@@ -324,10 +324,10 @@ int nvtb_vocab_from_arrays(nvtb_vocab_t** out, const int64_t* keys, const int64_
   v->info.n_kept = n;
   v->info.n_total = n;
   if (n > 0) {
-    NVTB_CUDA_OK(cudaMalloc(&v->keys, sizeof(int64_t) * n));
+    NVTB_CUDA_OK(cudaMallocAsync(&v->keys, sizeof(int64_t) * n, st));
     NVTB_CUDA_OK(cudaMemcpyAsync(v->keys, keys, sizeof(int64_t) * n, cudaMemcpyDeviceToDevice, st));
     if (sizes) {
-      NVTB_CUDA_OK(cudaMalloc(&v->sizes, sizeof(int64_t) * n));
+      NVTB_CUDA_OK(cudaMallocAsync(&v->sizes, sizeof(int64_t) * n, st));
       NVTB_CUDA_OK(cudaMemcpyAsync(v->sizes, sizes, sizeof(int64_t) * n, cudaMemcpyDeviceToDevice, st));
     }
   }
@@ -340,10 +340,11 @@ int nvtb_vocab_from_arrays(nvtb_vocab_t** out, const int64_t* keys, const int64_
 
 int nvtb_vocab_destroy(nvtb_vocab_t* v) {
   if (v == nullptr) return NVTB_OK;
-  cudaDeviceSynchronize();
-  if (v->t.slots) cudaFree(v->t.slots);
-  if (v->keys) cudaFree(v->keys);
-  if (v->sizes) cudaFree(v->sizes);
+  // stream-ordered frees on the legacy default stream: ordered after every kernel
+  // that may still probe the table, without a device-wide host sync
+  if (v->t.slots) cudaFreeAsync(v->t.slots, 0);
+  if (v->keys) cudaFreeAsync(v->keys, 0);
+  if (v->sizes) cudaFreeAsync(v->sizes, 0);
   delete v;
   return NVTB_OK;
 }
@@ -418,7 +419,7 @@ int nvtb_groupstats_create(nvtb_groupstats_t** out, const int64_t* keys, int64_t
   // the stats matrix may have more rows than keys (the null group's row)
   const int64_t n_rows = std::max<int64_t>(n_groups, null_row + 1);
   if (n_rows > 0) {
-    NVTB_CUDA_OK(cudaMalloc(&g->stats, sizeof(double) * n_rows * width));
+    NVTB_CUDA_OK(cudaMallocAsync(&g->stats, sizeof(double) * n_rows * width, st));
     NVTB_CUDA_OK(cudaMemcpyAsync(g->stats, stats, sizeof(double) * n_rows * width, cudaMemcpyDeviceToDevice, st));
   }
   int rc = lookup_create(&g->t, keys, n_groups, false, st);
@@ -430,9 +431,8 @@ int nvtb_groupstats_create(nvtb_groupstats_t** out, const int64_t* keys, int64_t
 
 int nvtb_groupstats_destroy(nvtb_groupstats_t* g) {
   if (g == nullptr) return NVTB_OK;
-  cudaDeviceSynchronize();
-  if (g->t.slots) cudaFree(g->t.slots);
-  if (g->stats) cudaFree(g->stats);
+  if (g->t.slots) cudaFreeAsync(g->t.slots, 0);
+  if (g->stats) cudaFreeAsync(g->stats, 0);
   delete g;
   return NVTB_OK;
 }

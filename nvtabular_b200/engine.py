@@ -252,6 +252,10 @@ class HashAgg:
         except Exception:
             pass
 
+    def reset(self):
+        _lib.check(self.lib.nvtb_hashagg_reset(self.h, _lib.stream_ptr()))
+        _count(2)
+
     def insert(self, key: Column, agg_cols: Sequence[Column] = ()):
         n = key.data.numel()
         assert len(agg_cols) == self.n_agg
@@ -260,12 +264,12 @@ class HashAgg:
         with _timed("hashagg_insert", _in_bytes([key]) + _in_bytes(agg_cols)):
             _lib.check(self.lib.nvtb_hashagg_insert(
                 self.h, _descs([key]), _descs(agg_cols) if self.n_agg else None, n, _lib.stream_ptr()))
-        _count(max(1, (n + (1 << 23) - 1) >> 23))
+        _count(1)
 
     def merge(self, keys: torch.Tensor, sizes: torch.Tensor, vals: Optional[torch.Tensor] = None):
         n = keys.numel()
         _lib.check(self.lib.nvtb_hashagg_merge(self.h, _ptr(keys), _ptr(sizes), _ptr(vals), n, _lib.stream_ptr()))
-        _count(max(1, (n + (1 << 23) - 1) >> 23) if n else 0)
+        _count(1 if n else 0)
 
     def add_null_group(self, size: int, vals: Optional[np.ndarray] = None):
         arr = _lib.double_array(list(vals)) if vals is not None and self.n_agg else None

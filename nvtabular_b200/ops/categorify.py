@@ -32,6 +32,13 @@ PAD_OFFSET, NULL_OFFSET, OOV_OFFSET = 0, 1, 2   # categorify.py:51-55
 EAGER_ARTIFACT_ROWS = 1 << 20                   # larger vocabularies are written lazily
 
 
+def _artifacts_lazy() -> bool:
+    """NVTB_ARTIFACTS=lazy defers the unique./meta. parquet files until a path is read
+    (`op.categories[name]`, Workflow.save, set_storage_path).  Default: eager, like the
+    reference, whose only fitted state IS those files."""
+    return os.environ.get("NVTB_ARTIFACTS", "eager").lower() == "lazy"
+
+
 def _make_name(*args, sep="_"):
     return sep.join(args)
 
@@ -96,8 +103,11 @@ class FittedVocab:
 
     def write(self, base_path, force=False):
         """categorify.py:731-822: unique.<name>.parquet (index = label) + meta.<name>.parquet."""
-        os.makedirs(base_path, exist_ok=True)
         self.path = "/".join([str(base_path), f"unique.{self.name}.parquet"])
+        if not force and _artifacts_lazy():
+            self._written = False
+            return self.path
+        os.makedirs(base_path, exist_ok=True)
         meta_path = "/".join([str(base_path), f"meta.{self.name}.parquet"])
         self.meta_frame().to_parquet(meta_path)
         if force or self.vocab.n_kept <= EAGER_ARTIFACT_ROWS:
@@ -188,6 +198,7 @@ class Categorify(StatOperator):
             warnings.warn("Performing a hash-based transformation. Do not expect Categorify to be "
                           "consistent on GPU and CPU with this num_buckets setting!")
         self._user_vocabs = vocabs
+        self._aggs = {}      # storage name -> engine.HashAgg, reused (reset) across fits
         self.vocabs = {}
         self.categories = _Categories()
         if vocabs is not None:
@@ -288,7 +299,11 @@ class Categorify(StatOperator):
             cols_all = [df[n] for df in parts for n in names]
             space = KeySpace.for_columns([_leaf(c) for c in cols_all]) if cols_all else KeySpace("int", None, np.dtype("int64"))
             key_names = [storage]
-        agg = engine.HashAgg(0)
+        agg = self._aggs.get(storage)
+        if agg is None:
+            agg = self._aggs[storage] = engine.HashAgg(0)
+        else:
+            agg.reset()
         for df in parts:
             if combo:
                 agg.insert(space.keys_for([df[n] for n in names]))
