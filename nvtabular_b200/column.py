@@ -122,6 +122,39 @@ class Column:
     def with_data(self, data, validity=None, keep_list=True) -> "Column":
         return Column(data, validity, self.offsets if keep_list else None, None)
 
+    def to(self, device, non_blocking=True) -> "Column":
+        """Copy the buffers to `device` (pinned host <-> HBM copies are asynchronous)."""
+        out = Column(self.data.to(device, non_blocking=non_blocking),
+                     self.validity.to(device, non_blocking=non_blocking) if self.validity is not None else None,
+                     self.offsets.to(device, non_blocking=non_blocking) if self.offsets is not None else None,
+                     self.dictionary, self.fill, self.is_bool)
+        out.prehashed = self.prehashed
+        return out
+
+    def pin(self) -> "Column":
+        """A pinned-host copy (the staging format of the end-to-end path)."""
+        def _p(t):
+            if t is None:
+                return None
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t)
+            return buf
+        out = Column(_p(self.data), _p(self.validity), _p(self.offsets), self.dictionary, self.fill, self.is_bool)
+        out.prehashed = self.prehashed
+        return out
+
+    @property
+    def device(self):
+        return self.data.device
+
+    def nbytes(self) -> int:
+        n = self.data.numel() * self.data.element_size()
+        if self.validity is not None:
+            n += self.validity.numel()
+        if self.offsets is not None:
+            n += self.offsets.numel() * 8
+        return n
+
     def null_count(self) -> int:
         if self.validity is None:
             return 0
@@ -294,6 +327,39 @@ class DeviceFrame:
 
     def copy(self) -> "DeviceFrame":
         return DeviceFrame(dict(self._cols))
+
+    def slice_rows(self, start: int, stop: int) -> "DeviceFrame":
+        """Rows [start, stop) as views; `start` must be a multiple of 64 (keeps the 32-byte
+        alignment of the data and the byte alignment of the validity bitmask)."""
+        assert start % 64 == 0, "partition boundaries must be multiples of 64 rows"
+        out = {}
+        for k, c in self._cols.items():
+            assert c.offsets is None, "list columns cannot be row-sliced"
+            v = None
+            if c.validity is not None:
+                nb = (stop - start + 7) // 8
+                v = c.validity[start // 8: start // 8 + ((nb + 31) // 32) * 32]
+                if v.numel() < nb:
+                    v = c.validity[start // 8: start // 8 + nb]
+            col = Column(c.data[start:stop], v, None, c.dictionary, c.fill, c.is_bool)
+            col.prehashed = c.prehashed
+            out[k] = col
+        return DeviceFrame(out)
+
+    def to(self, device, non_blocking=True) -> "DeviceFrame":
+        return DeviceFrame({k: c.to(device, non_blocking) for k, c in self._cols.items()})
+
+    def pin(self) -> "DeviceFrame":
+        return DeviceFrame({k: c.pin() for k, c in self._cols.items()})
+
+    @property
+    def is_host(self) -> bool:
+        for c in self._cols.values():
+            return c.data.device.type == "cpu"
+        return False
+
+    def nbytes(self) -> int:
+        return sum(c.nbytes() for c in self._cols.values())
 
     def drop(self, names) -> "DeviceFrame":
         return DeviceFrame({k: v for k, v in self._cols.items() if k not in set(names)})

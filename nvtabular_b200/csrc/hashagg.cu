@@ -36,13 +36,11 @@
 
 namespace nvtb {
 
-constexpr int kSmemSlots = 4096;   // per-CTA pre-aggregation table
 constexpr int kSmemProbes = 4;
-constexpr int kInsertSmemBytes = kSmemSlots * (int)(sizeof(long long) + sizeof(unsigned int));
 constexpr int kMaxProbes = 128;    // global probe limit before a pair is refused
 constexpr int64_t kSampleRows = (int64_t)1 << 20;
-constexpr int64_t kMinCapacity = 1 << 12;
-constexpr int kInsertCtasPerSm = 4;
+constexpr int64_t kMinCapacity = 1 << 16;
+constexpr int kInsertCtasPerSm = 3;
 
 // min/max are kept as order-preserving int64 images of the double so that the
 // native 64-bit atomicMin/atomicMax can be used.
@@ -66,17 +64,27 @@ __host__ __device__ __forceinline__ double dec_ordered(int64_t e) {
 constexpr int64_t kMinInit = INT64_MAX;
 constexpr int64_t kMaxInit = INT64_MIN;
 
+// Two slot layouts:
+//   wide   (16 B)  {int64 key, int64 size}; empty key = INT64_MIN
+//   narrow ( 8 B)  (uint32 size << 32) | uint32 key; empty = 0 (a live slot has
+//                  size >= 1).  Used for int32 keys without payload while the
+//                  handle has seen < 2^32 rows: half the footprint (tables of a
+//                  few million keys stay L2-resident), a new key costs ONE
+//                  64-bit CAS that also deposits the count, a known key one
+//                  32-bit RED.
 struct Table {
-  int64_t* slots;   // [2*capacity] {key, size}
-  double* vals;     // [capacity * 4 * n_agg] or nullptr
+  int64_t* slots;   // wide: [2*capacity]; narrow: [capacity] packed words
+  double* vals;     // [capacity * 4 * n_agg] or nullptr (wide only)
   int64_t capacity; // power of two
   int n_agg;
+  int narrow;
 };
 
 struct Counters {
   unsigned long long n_unique;   // distinct keys in the table
   unsigned long long size[2];    // special groups: [0] null key, [1] INT64_MIN key
   unsigned long long ovf_count;  // pairs refused into the arena by the pending launch
+  long long budget;              // new keys the current launch may still claim (load <= 0.5)
 };
 
 struct Arena {
@@ -116,59 +124,107 @@ __device__ __forceinline__ void vals_combine(double* __restrict__ dst,
   if (mx == mx) atomicMax(reinterpret_cast<long long*>(dst + 3), (long long)enc_ordered(mx));
 }
 
-// find the slot of `key`, claiming an empty one if the thread still has budget
-// for new keys.  Returns -1 when the pair has to be refused (budget exhausted or
-// kMaxProbes slots inspected).  key != kEmptyKey.
-__device__ __forceinline__ int64_t table_upsert(const Table& t, int64_t key,
-                                                int64_t& budget, unsigned& n_new) {
-  const int64_t mask = t.capacity - 1;
-  int64_t slot = (int64_t)(table_mix64((uint64_t)key) & (uint64_t)mask);
-#pragma unroll 1
-  for (int probe = 0; probe < kMaxProbes; ++probe) {
-    long long* kp = reinterpret_cast<long long*>(t.slots + 2 * slot);
-    long long cur = __ldcg(kp);
-    if (cur == key) return slot;
-    if (cur == kEmptyKey) {
-      if (budget <= 0) return -1;
-      long long prev = (long long)atomicCAS(
-          reinterpret_cast<unsigned long long*>(kp),
-          (unsigned long long)kEmptyKey, (unsigned long long)key);
-      if (prev == kEmptyKey) {
-        --budget;
-        ++n_new;
-        return slot;
-      }
-      if (prev == key) return slot;
-    }
-    slot = (slot + 1) & mask;
-  }
-  return -1;
+template <bool NARROW>
+__device__ __forceinline__ unsigned long long slot_load(const Table& t, int64_t slot) {
+  const unsigned long long* p = reinterpret_cast<const unsigned long long*>(t.slots) + (NARROW ? slot : 2 * slot);
+  return __ldcg(p);
 }
 
-__device__ __forceinline__ void table_add_size(const Table& t, int64_t slot,
-                                               int64_t add) {
-  atomicAdd(reinterpret_cast<unsigned long long*>(t.slots + 2 * slot + 1),
-            (unsigned long long)add);
-}
-
-// warp-aggregated append of one refused pair (divergent callers allowed)
+// append one refused pair (rare path: a plain atomic, safe under any divergence)
 __device__ __forceinline__ int64_t arena_claim(Counters* ctr) {
-  const unsigned active = __activemask();
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(active) - 1;
-  unsigned long long base = 0;
-  if (lane == leader) base = atomicAdd(&ctr->ovf_count, (unsigned long long)__popc(active));
-  base = __shfl_sync(active, base, leader);
-  return (int64_t)base + __popc(active & ((1u << lane) - 1u));
+  return (int64_t)atomicAdd(&ctr->ovf_count, 1ull);
 }
 
-__device__ __forceinline__ void upsert_size(const Table& t, const Arena& a, Counters* ctr,
-                                            int64_t key, int64_t add, int64_t& budget,
-                                            unsigned& n_new) {
-  const int64_t slot = table_upsert(t, key, budget, n_new);
-  if (slot >= 0) {
-    table_add_size(t, slot, add);
+// Fold (key, add) into the table starting from a PREFETCHED first probe
+// (`slot`, `word`): callers issue the first-probe loads of several keys back to
+// back and only then resolve them, so a thread keeps up to 8 table reads in
+// flight.  The common case (first probe finds the key) is a handful of inlined
+// instructions; everything else (claiming a new key, walking the probe sequence)
+// lives in ONE out-of-line copy so the kernel stays small enough for the
+// instruction cache even though 16 rows are unrolled per thread.
+// Returns the slot, or -1 when kMaxProbes slots were inspected (pair refused).
+// There is no load-factor guard: a table that is too small simply fills up, probes
+// start failing, refused pairs go to the arena and settle() regrows the table.
+template <bool NARROW>
+__device__ __noinline__ int64_t upsert_slow(const Table& t, int64_t key, int64_t add,
+                                            int64_t slot, unsigned long long word, unsigned& n_new) {
+  const int64_t mask = t.capacity - 1;
+  unsigned long long* base = reinterpret_cast<unsigned long long*>(t.slots);
+  int64_t result = -1;
+  bool done = false;
+#pragma unroll 1
+  for (int probe = 0; probe < kMaxProbes && !done; ++probe) {
+    if (NARROW) {
+      bool match = (word != 0ull) && ((unsigned)word == (unsigned)key);
+      if (word == 0ull) {
+        const unsigned long long want =
+            ((unsigned long long)(unsigned)add << 32) | (unsigned long long)(unsigned)key;
+        const unsigned long long prev = atomicCAS(base + slot, 0ull, want);
+        if (prev == 0ull) { ++n_new; result = slot; done = true; }   // the CAS deposited the count
+        else match = ((unsigned)prev == (unsigned)key);              // lost the race, maybe to the same key
+      }
+      if (match && !done) {
+        atomicAdd(reinterpret_cast<unsigned*>(base + slot) + 1, (unsigned)add);
+        result = slot; done = true;
+      }
+    } else {
+      bool match = ((long long)word == key);
+      if ((long long)word == kEmptyKey) {
+        const unsigned long long prev = atomicCAS(base + 2 * slot, (unsigned long long)kEmptyKey,
+                                                  (unsigned long long)key);
+        if ((long long)prev == kEmptyKey) { ++n_new; match = true; }
+        else match = ((long long)prev == key);
+      }
+      if (match && !done) {
+        atomicAdd(base + 2 * slot + 1, (unsigned long long)add);
+        result = slot; done = true;
+      }
+    }
+    if (!done) {
+      slot = (slot + 1) & mask;
+      word = slot_load<NARROW>(t, slot);
+    }
+  }
+  return result;
+}
+
+template <bool NARROW>
+__device__ __forceinline__ int64_t upsert_add(const Table& t, Counters*, int64_t key, int64_t add,
+                                              int64_t slot, unsigned long long word,
+                                              int64_t&, unsigned& n_new) {
+  unsigned long long* base = reinterpret_cast<unsigned long long*>(t.slots);
+  if (NARROW) {
+    if (word != 0ull && (unsigned)word == (unsigned)key) {
+      atomicAdd(reinterpret_cast<unsigned*>(base + slot) + 1, (unsigned)add);
+      return slot;
+    }
   } else {
+    if ((long long)word == key) {
+      atomicAdd(base + 2 * slot + 1, (unsigned long long)add);
+      return slot;
+    }
+  }
+  return upsert_slow<NARROW>(t, key, add, slot, word, n_new);
+}
+
+__device__ __forceinline__ int64_t first_slot(const Table& t, int64_t key) {
+  return (int64_t)(table_mix64((uint64_t)key) & (uint64_t)(t.capacity - 1));
+}
+
+// one-key convenience forms (cold paths: merge, flush)
+template <bool NARROW>
+__device__ __forceinline__ int64_t upsert_one(const Table& t, Counters* ctr, int64_t key, int64_t add,
+                                              int64_t& budget, unsigned& n_new) {
+  const int64_t slot = first_slot(t, key);
+  return upsert_add<NARROW>(t, ctr, key, add, slot, slot_load<NARROW>(t, slot), budget, n_new);
+}
+
+template <bool NARROW>
+__device__ __forceinline__ void upsert_or_spill(const Table& t, const Arena& a, Counters* ctr,
+                                                int64_t key, int64_t add, int64_t slot,
+                                                unsigned long long word, int64_t& budget,
+                                                unsigned& n_new) {
+  if (upsert_add<NARROW>(t, ctr, key, add, slot, word, budget, n_new) < 0) {
     const int64_t o = arena_claim(ctr);
     if (o < a.cap) { a.keys[o] = key; a.sizes[o] = add; }
   }
@@ -178,6 +234,7 @@ __global__ void table_init_kernel(Table t) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
        s < t.capacity; s += stride) {
+    if (t.narrow) { t.slots[s] = 0; continue; }
     t.slots[2 * s] = kEmptyKey;
     t.slots[2 * s + 1] = 0;
     for (int j = 0; j < t.n_agg; ++j) {
@@ -189,9 +246,14 @@ __global__ void table_init_kernel(Table t) {
   }
 }
 
+__global__ void arm_launch_kernel(Counters* ctr, long long budget) {
+  ctr->ovf_count = 0ull;
+  ctr->budget = budget;
+}
+
 __global__ void special_init_kernel(Counters* ctr, double* special_vals, int n_agg) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    ctr->n_unique = 0; ctr->size[0] = 0; ctr->size[1] = 0; ctr->ovf_count = 0;
+    ctr->n_unique = 0; ctr->size[0] = 0; ctr->size[1] = 0; ctr->ovf_count = 0; ctr->budget = 0;
     for (int g = 0; g < 2; ++g)
       for (int j = 0; j < n_agg; ++j) {
         double* v = special_vals + (g * n_agg + j) * 4;
@@ -205,59 +267,147 @@ __global__ void special_init_kernel(Counters* ctr, double* special_vals, int n_a
 // ---------------------------------------------------------------------------
 // insert, keys only (Categorify)
 // ---------------------------------------------------------------------------
-template <typename KeyT>
-__global__ void __launch_bounds__(kThreads)
+// Per-CTA shared-memory pre-aggregation table.
+//   int32 keys: 8192 packed slots (count << 32 | key; 0 = empty), 64 KB
+//   int64 keys: 4096 slots of {int64 key, uint32 count}, 48 KB
+template <typename KeyT> struct SmemAgg;
+
+template <> struct SmemAgg<int32_t> {
+  static constexpr int kSlots = 8192;
+  static constexpr int kBytes = kSlots * 8;
+  unsigned long long* w;
+  __device__ __forceinline__ explicit SmemAgg(unsigned char* raw) : w(reinterpret_cast<unsigned long long*>(raw)) {}
+  __device__ __forceinline__ void clear() {
+    for (int s = threadIdx.x; s < kSlots; s += kThreads) w[s] = 0ull;
+  }
+  __device__ __noinline__ bool fold_slow(unsigned key, unsigned s) {
+    bool done = false;
+#pragma unroll 1
+    for (int p = 0; p < kSmemProbes && !done; ++p) {
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&w[s]);
+      if (cur == 0ull) {
+        cur = atomicCAS(&w[s], 0ull, (1ull << 32) | (unsigned long long)key);
+        if (cur == 0ull) done = true;                      // claimed with count 1
+      }
+      if (!done && (unsigned)cur == key && cur != 0ull) {
+        atomicAdd(reinterpret_cast<unsigned*>(&w[s]) + 1, 1u);
+        done = true;
+      }
+      s = (s + 1) & (kSlots - 1);
+    }
+    return done;
+  }
+  // fold one key; true = absorbed.  `hits` counts keys that were already present.
+  __device__ __forceinline__ bool fold(long long k, uint64_t h, unsigned& hits) {
+    const unsigned key = (unsigned)(int)k;
+    const unsigned s = (unsigned)(h >> 40) & (kSlots - 1);   // bits disjoint from the global slot bits
+    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&w[s]);
+    if (cur != 0ull && (unsigned)cur == key) {
+      atomicAdd(reinterpret_cast<unsigned*>(&w[s]) + 1, 1u);
+      hits++;
+      return true;
+    }
+    return fold_slow(key, s);
+  }
+  __device__ __forceinline__ bool get(int s, long long* key, unsigned* cnt) const {
+    const unsigned long long cur = w[s];
+    *key = (long long)(int)(unsigned)cur;
+    *cnt = (unsigned)(cur >> 32);
+    return cur != 0ull;
+  }
+};
+
+template <> struct SmemAgg<int64_t> {
+  static constexpr int kSlots = 4096;
+  static constexpr int kBytes = kSlots * 12;
+  long long* keys;
+  unsigned* cnt;
+  __device__ __forceinline__ explicit SmemAgg(unsigned char* raw)
+      : keys(reinterpret_cast<long long*>(raw)), cnt(reinterpret_cast<unsigned*>(raw + sizeof(long long) * kSlots)) {}
+  __device__ __forceinline__ void clear() {
+    for (int s = threadIdx.x; s < kSlots; s += kThreads) { keys[s] = kEmptyKey; cnt[s] = 0u; }
+  }
+  __device__ __noinline__ bool fold_slow(long long k, unsigned s) {
+    bool done = false;
+#pragma unroll 1
+    for (int p = 0; p < kSmemProbes && !done; ++p) {
+      long long cur = *reinterpret_cast<volatile long long*>(&keys[s]);
+      if (cur == kEmptyKey)
+        cur = (long long)atomicCAS(reinterpret_cast<unsigned long long*>(&keys[s]),
+                                   (unsigned long long)kEmptyKey, (unsigned long long)k);
+      if (cur == kEmptyKey || cur == k) {
+        atomicAdd(&cnt[s], 1u);
+        done = true;
+      }
+      s = (s + 1) & (kSlots - 1);
+    }
+    return done;
+  }
+  __device__ __forceinline__ bool fold(long long k, uint64_t h, unsigned& hits) {
+    const unsigned s = (unsigned)(h >> 40) & (kSlots - 1);
+    if (*reinterpret_cast<volatile long long*>(&keys[s]) == k) {
+      atomicAdd(&cnt[s], 1u);
+      hits++;
+      return true;
+    }
+    return fold_slow(k, s);
+  }
+  __device__ __forceinline__ bool get(int s, long long* key, unsigned* c) const {
+    *key = keys[s];
+    *c = cnt[s];
+    return keys[s] != kEmptyKey;
+  }
+};
+
+template <typename KeyT, bool NARROW>
+__global__ void __launch_bounds__(kThreads, 3)
 insert_keys_kernel(const KeyT* __restrict__ keys,
                    const uint8_t* __restrict__ mask, int64_t n, Table t,
-                   Counters* ctr, Arena arena, int64_t thread_budget) {
-  // 48 KB of dynamic shared memory: keys[4096] (8 B) then counts[4096] (4 B)
+                   Counters* ctr, Arena arena, int64_t /*unused*/) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  long long* skeys = reinterpret_cast<long long*>(smem_raw);
-  unsigned int* scnt = reinterpret_cast<unsigned int*>(smem_raw + sizeof(long long) * kSmemSlots);
+  SmemAgg<KeyT> sm(smem_raw);
   __shared__ unsigned long long s_null, s_min;
   __shared__ unsigned int s_hits, s_rows, s_new;
   __shared__ int s_bypass;
-  for (int s = threadIdx.x; s < kSmemSlots; s += kThreads) {
-    skeys[s] = kEmptyKey;
-    scnt[s] = 0u;
-  }
+  sm.clear();
   if (threadIdx.x == 0) { s_null = 0ull; s_min = 0ull; s_hits = 0u; s_rows = 0u; s_new = 0u; s_bypass = 0; }
   __syncthreads();
 
   unsigned int n_null = 0, n_min = 0, n_new = 0;
-  int64_t budget = thread_budget;
+  int64_t budget = 0;
   bool bypass = false;
   const bool aligned = is_aligned32(keys);
 
-  auto fold = [&](KeyT x, bool valid, unsigned& hits, unsigned& rows) {
-    if (!valid) { n_null++; return; }
-    const long long k = (long long)x;
-    if (sizeof(KeyT) == 8 && k == kEmptyKey) { n_min++; return; }
-    rows++;
-    if (!bypass) {
-      const uint64_t h = table_mix64((uint64_t)k);
-      // upper hash bits pick the smem slot, independent of the global slot bits
-      unsigned s = (unsigned)(h >> 40) & (kSmemSlots - 1);
+  // 8 rows of one lane: (1) shared-memory fold, (2) first-probe loads of every key
+  // that still has to reach the global table, issued back to back, (3) resolve
+  auto fold8 = [&](const KeyT (&v)[kRows], unsigned m, unsigned& hits, unsigned& rows) {
+    unsigned pend = 0;
 #pragma unroll
-      for (int p = 0; p < kSmemProbes; ++p) {
-        long long cur = *reinterpret_cast<volatile long long*>(&skeys[s]);
-        if (cur == k) {
-          atomicAdd(&scnt[s], 1u);
-          hits++;
-          return;
-        }
-        if (cur == kEmptyKey) {
-          cur = (long long)atomicCAS(reinterpret_cast<unsigned long long*>(&skeys[s]),
-                                     (unsigned long long)kEmptyKey, (unsigned long long)k);
-          if (cur == kEmptyKey || cur == k) {
-            atomicAdd(&scnt[s], 1u);
-            return;
-          }
-        }
-        s = (s + 1) & (kSmemSlots - 1);
+    for (int k = 0; k < kRows; ++k) {
+      const bool valid = (m >> k) & 1u;
+      const long long key = (long long)v[k];
+      const bool is_min = valid && sizeof(KeyT) == 8 && key == kEmptyKey;
+      n_null += valid ? 0u : 1u;
+      n_min += is_min ? 1u : 0u;
+      if (valid && !is_min) {
+        rows++;
+        if (bypass || !sm.fold(key, table_mix64((uint64_t)key), hits)) pend |= 1u << k;
       }
     }
-    upsert_size(t, arena, ctr, k, 1, budget, n_new);
+    if (pend != 0) {
+      int64_t slot[kRows];
+      unsigned long long word[kRows];
+#pragma unroll
+      for (int k = 0; k < kRows; ++k)
+        if ((pend >> k) & 1u) {
+          slot[k] = first_slot(t, (long long)v[k]);
+          word[k] = slot_load<NARROW>(t, slot[k]);
+        }
+#pragma unroll
+      for (int k = 0; k < kRows; ++k)
+        if ((pend >> k) & 1u)
+          upsert_or_spill<NARROW>(t, arena, ctr, (long long)v[k], 1, slot[k], word[k], budget, n_new);
+    }
   };
 
   const int64_t n_tiles = (n + kTile - 1) / kTile;
@@ -275,13 +425,18 @@ insert_keys_kernel(const KeyT* __restrict__ keys,
         m[g] = valid8(mask, i);
       }
 #pragma unroll
-      for (int g = 0; g < kGroups; ++g)
-#pragma unroll
-        for (int k = 0; k < kRows; ++k) fold(v[g][k], (m[g] >> k) & 1u, hits, rows);
+      for (int g = 0; g < kGroups; ++g) fold8(v[g], m[g], hits, rows);
     } else {
       const int64_t end = (base + kTile < n) ? base + kTile : n;
-      for (int64_t i = base + threadIdx.x; i < end; i += kThreads)
-        fold(keys[i], valid1(mask, i), hits, rows);
+      for (int64_t i = base + threadIdx.x; i < end; i += kThreads) {
+        if (!valid1(mask, i)) { n_null++; continue; }
+        const long long key = (long long)keys[i];
+        if (sizeof(KeyT) == 8 && key == kEmptyKey) { n_min++; continue; }
+        rows++;
+        if (!bypass && sm.fold(key, table_mix64((uint64_t)key), hits)) continue;
+        const int64_t sl = first_slot(t, key);
+        upsert_or_spill<NARROW>(t, arena, ctr, key, 1, sl, slot_load<NARROW>(t, sl), budget, n_new);
+      }
     }
     if (first) {
       // after its first tile the CTA decides whether shared-memory folding pays:
@@ -300,9 +455,24 @@ insert_keys_kernel(const KeyT* __restrict__ keys,
   if (n_min) atomicAdd(&s_min, (unsigned long long)n_min);
   __syncthreads();
   // flush the CTA-local aggregates: one global update per distinct key per CTA
-  for (int s = threadIdx.x; s < kSmemSlots; s += kThreads) {
-    const long long k = skeys[s];
-    if (k != kEmptyKey) upsert_size(t, arena, ctr, k, (int64_t)scnt[s], budget, n_new);
+  for (int s0 = 0; s0 < SmemAgg<KeyT>::kSlots; s0 += kThreads * 4) {
+    long long k[4];
+    unsigned c[4];
+    bool live[4];
+    int64_t slot[4];
+    unsigned long long word[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      live[j] = sm.get(s0 + j * kThreads + threadIdx.x, &k[j], &c[j]);
+      if (live[j]) {
+        slot[j] = first_slot(t, k[j]);
+        word[j] = slot_load<NARROW>(t, slot[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (live[j])
+        upsert_or_spill<NARROW>(t, arena, ctr, k[j], (int64_t)c[j], slot[j], word[j], budget, n_new);
   }
   if (n_new) atomicAdd(&s_new, n_new);
   __syncthreads();
@@ -346,7 +516,8 @@ insert_agg_kernel(const KeyT* __restrict__ keys,
                   Table t, Counters* ctr, double* special_vals, Arena arena,
                   int64_t thread_budget) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t budget = thread_budget;
+  int64_t budget = 0;   // drawn from ctr->budget in chunks
+  (void)thread_budget;
   unsigned n_new = 0;
   const double nan = __longlong_as_double(0x7FF8000000000000ll);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -361,9 +532,8 @@ insert_agg_kernel(const KeyT* __restrict__ keys,
       atomicAdd(&ctr->size[1], 1ull);
       vdst = special_vals + (int64_t)t.n_agg * 4;
     } else {
-      const int64_t slot = table_upsert(t, k, budget, n_new);
+      const int64_t slot = upsert_one<false>(t, ctr, k, 1, budget, n_new);
       if (slot >= 0) {
-        table_add_size(t, slot, 1);
         vdst = t.vals + slot * t.n_agg * 4;
       } else {
         const int64_t o = arena_claim(ctr);
@@ -389,22 +559,24 @@ insert_agg_kernel(const KeyT* __restrict__ keys,
 }
 
 // merge pre-aggregated rows (other GPUs' partials, or a drained arena)
+template <bool NARROW>
 __global__ void __launch_bounds__(kThreads)
 merge_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes,
              const double* __restrict__ vals, int64_t n, Table t, Counters* ctr,
              double* special_vals, Arena arena, int64_t thread_budget) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t budget = thread_budget;
+  int64_t budget = 0;   // drawn from ctr->budget in chunks
+  (void)thread_budget;
   unsigned n_new = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += stride) {
     const long long k = keys[i];
     double* vdst;
-    if (k == kEmptyKey) {
+    if (!NARROW && k == kEmptyKey) {
       atomicAdd(&ctr->size[1], (unsigned long long)sizes[i]);
       vdst = special_vals + (int64_t)t.n_agg * 4;
     } else {
-      const int64_t slot = table_upsert(t, k, budget, n_new);
+      const int64_t slot = upsert_one<NARROW>(t, ctr, k, sizes[i], budget, n_new);
       if (slot < 0) {
         const int64_t o = arena_claim(ctr);
         if (o < arena.cap) {
@@ -416,10 +588,9 @@ merge_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes
         }
         continue;
       }
-      table_add_size(t, slot, sizes[i]);
-      vdst = t.vals + slot * t.n_agg * 4;
+      vdst = NARROW ? nullptr : t.vals + slot * t.n_agg * 4;
     }
-    if (vals != nullptr)
+    if (vals != nullptr && vdst != nullptr)
       for (int j = 0; j < t.n_agg; ++j) {
         const double* v = vals + (i * t.n_agg + j) * 4;
         vals_combine(vdst + j * 4, v[0], v[1], v[2], v[3]);
@@ -428,27 +599,39 @@ merge_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes
   if (n_new) atomicAdd(&ctr->n_unique, (unsigned long long)n_new);
 }
 
-// rehash an old table into a new, larger one (keys are distinct: plain stores
-// after the claim; n_unique is unchanged)
+// rehash an old table into a new one (larger, and/or narrow -> wide).  Keys are
+// distinct: plain stores after the claim; n_unique is unchanged.  The new table is
+// at most half full, so the probe loop terminates.
 __global__ void __launch_bounds__(kThreads)
 rehash_kernel(Table old_t, Table new_t) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t mask = new_t.capacity - 1;
+  unsigned long long* nb = reinterpret_cast<unsigned long long*>(new_t.slots);
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
        s < old_t.capacity; s += stride) {
-    const long long k = old_t.slots[2 * s];
-    if (k == kEmptyKey) continue;
-    int64_t slot = (int64_t)(table_mix64((uint64_t)k) & (uint64_t)mask);
-    while (true) {  // the new table is at most half full: terminates
-      long long prev = (long long)atomicCAS(
-          reinterpret_cast<unsigned long long*>(new_t.slots + 2 * slot),
-          (unsigned long long)kEmptyKey, (unsigned long long)k);
-      if (prev == kEmptyKey) break;
-      slot = (slot + 1) & mask;
+    long long k, sz;
+    if (old_t.narrow) {
+      const unsigned long long w = (unsigned long long)old_t.slots[s];
+      if (w == 0ull) continue;
+      k = (long long)(int)(unsigned)w;
+      sz = (long long)(w >> 32);
+    } else {
+      k = old_t.slots[2 * s];
+      if (k == kEmptyKey) continue;
+      sz = old_t.slots[2 * s + 1];
     }
-    new_t.slots[2 * slot + 1] = old_t.slots[2 * s + 1];
-    for (int j = 0; j < old_t.n_agg * 4; ++j)
-      new_t.vals[slot * old_t.n_agg * 4 + j] = old_t.vals[s * old_t.n_agg * 4 + j];
+    int64_t slot = (int64_t)(table_mix64((uint64_t)k) & (uint64_t)mask);
+    if (new_t.narrow) {
+      const unsigned long long want = ((unsigned long long)sz << 32) | (unsigned long long)(unsigned)k;
+      while (atomicCAS(nb + slot, 0ull, want) != 0ull) slot = (slot + 1) & mask;
+    } else {
+      while ((long long)atomicCAS(nb + 2 * slot, (unsigned long long)kEmptyKey, (unsigned long long)k) != kEmptyKey)
+        slot = (slot + 1) & mask;
+      new_t.slots[2 * slot + 1] = sz;
+      if (!old_t.narrow)
+        for (int j = 0; j < old_t.n_agg * 4; ++j)
+          new_t.vals[slot * old_t.n_agg * 4 + j] = old_t.vals[s * old_t.n_agg * 4 + j];
+    }
   }
 }
 
@@ -462,8 +645,18 @@ export_kernel(Table t, int64_t* __restrict__ keys_out,
   // capacity is a power of two >= 4096, so every warp runs the same trip count
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
        s < t.capacity; s += stride) {
-    const long long k = t.slots[2 * s];
-    const bool live = (k != kEmptyKey);
+    long long k, sz = 0;
+    bool live;
+    if (t.narrow) {
+      const unsigned long long w = (unsigned long long)t.slots[s];
+      live = (w != 0ull);
+      k = (long long)(int)(unsigned)w;
+      sz = (long long)(w >> 32);
+    } else {
+      k = t.slots[2 * s];
+      live = (k != kEmptyKey);
+      if (live) sz = t.slots[2 * s + 1];
+    }
     const unsigned ballot = __ballot_sync(0xffffffffu, live);
     if (ballot == 0) continue;
     unsigned long long base = 0;
@@ -472,7 +665,7 @@ export_kernel(Table t, int64_t* __restrict__ keys_out,
     if (live) {
       const int64_t o = (int64_t)base + __popc(ballot & ((1u << lane) - 1u));
       keys_out[o] = k;
-      if (sizes_out) sizes_out[o] = t.slots[2 * s + 1];
+      if (sizes_out) sizes_out[o] = sz;
       if (vals_out)
         for (int j = 0; j < t.n_agg; ++j) {
           const double* v = t.vals + (s * t.n_agg + j) * 4;
@@ -579,12 +772,13 @@ static int plain_grid(int64_t n) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
 }
 
-static int table_alloc(Table* t, int64_t capacity, int n_agg, cudaStream_t st) {
+static int table_alloc(Table* t, int64_t capacity, int n_agg, bool narrow, cudaStream_t st) {
   t->capacity = capacity;
   t->n_agg = n_agg;
+  t->narrow = narrow ? 1 : 0;
   t->slots = nullptr;
   t->vals = nullptr;
-  NVTB_CUDA_OK(cudaMallocAsync(&t->slots, sizeof(int64_t) * 2 * capacity, st));
+  NVTB_CUDA_OK(cudaMallocAsync(&t->slots, sizeof(int64_t) * (narrow ? 1 : 2) * capacity, st));
   if (n_agg > 0)
     NVTB_CUDA_OK(cudaMallocAsync(&t->vals, sizeof(double) * 4 * n_agg * capacity, st));
   table_init_kernel<<<plain_grid(capacity), kThreads, 0, st>>>(*t);
@@ -697,10 +891,13 @@ static double estimate_cardinality(double U, double s) {
   return lo;
 }
 
-static int grow_to(nvtb_hashagg* h, int64_t new_cap, cudaStream_t st) {
-  if (new_cap <= h->t.capacity) return NVTB_OK;
+// move to a table of `new_cap` slots and/or the other layout (narrow -> wide only)
+static int grow_to(nvtb_hashagg* h, int64_t new_cap, cudaStream_t st, bool force_wide = false) {
+  const bool narrow = h->t.narrow && !force_wide;
+  new_cap = std::max(new_cap, h->t.capacity);
+  if (new_cap == h->t.capacity && narrow == (bool)h->t.narrow) return NVTB_OK;
   Table nt;
-  int rc = table_alloc(&nt, new_cap, h->n_agg, st);
+  int rc = table_alloc(&nt, new_cap, h->n_agg, narrow, st);
   if (rc) return rc;
   if (h->u_known > 0 || h->rows_total > 0) {
     rehash_kernel<<<plain_grid(h->t.capacity), kThreads, 0, st>>>(h->t, nt);
@@ -715,10 +912,14 @@ static int grow_to(nvtb_hashagg* h, int64_t new_cap, cudaStream_t st) {
 static int launch_merge(nvtb_hashagg* h, const int64_t* keys, const int64_t* sizes,
                         const double* vals, int64_t n, const Arena& arena, cudaStream_t st) {
   const int grid = plain_grid(n);
-  const int64_t room = h->t.capacity / 2 - h->u_known;
-  const int64_t budget = std::max<int64_t>(0, room) / ((int64_t)grid * kThreads);
-  merge_kernel<<<grid, kThreads, 0, st>>>(keys, sizes, vals, n, h->t, h->ctr, h->special_vals,
-                                         arena, budget);
+  const int64_t room = std::max<int64_t>(0, h->t.capacity / 2 - h->u_known);
+  const int64_t budget = 0;
+  arm_launch_kernel<<<1, 1, 0, st>>>(h->ctr, (long long)room);
+  NVTB_LAUNCH_OK();
+  if (h->t.narrow)
+    merge_kernel<true><<<grid, kThreads, 0, st>>>(keys, sizes, vals, n, h->t, h->ctr, h->special_vals, arena, budget);
+  else
+    merge_kernel<false><<<grid, kThreads, 0, st>>>(keys, sizes, vals, n, h->t, h->ctr, h->special_vals, arena, budget);
   NVTB_LAUNCH_OK();
   return NVTB_OK;
 }
@@ -740,9 +941,8 @@ static int settle(nvtb_hashagg* h) {
       // every refused pair may be a new key: size for all of them at load <= 0.25
       int rc = grow_to(h, next_pow2(4 * (h->u_known + ovf)), st);
       if (rc) return rc;
-      NVTB_CUDA_OK(cudaMemsetAsync(&h->ctr->ovf_count, 0, sizeof(unsigned long long), st));
-      // budget: capacity/2 - u_known >= ovf, spread over the launch's threads; a pair the
-      // per-thread budget still refuses lands in a fresh arena and is settled by the loop
+      // budget: capacity/2 - u_known >= u_known + 2*ovf; a pair that is still refused (128
+      // probes) lands in a fresh private arena and is settled by the loop
       rc = arena_alloc(&h->arena, ovf, h->n_agg, st);
       if (rc) return rc;
       rc = launch_merge(h, old.keys, old.sizes, old.vals, ovf, h->arena, st);
@@ -790,18 +990,25 @@ static int launch_insert(nvtb_hashagg* h, const KeyT* kp, const uint8_t* mp, con
                          int64_t m, cudaStream_t st) {
   int rc = arena_acquire(h, &h->arena, m, h->n_agg);
   if (rc) return rc;
-  NVTB_CUDA_OK(cudaMemsetAsync(&h->ctr->ovf_count, 0, sizeof(unsigned long long), st));
   const int64_t room = std::max<int64_t>(0, h->t.capacity / 2 - h->u_known);
+  arm_launch_kernel<<<1, 1, 0, st>>>(h->ctr, (long long)room);
+  NVTB_LAUNCH_OK();
   if (h->n_agg == 0) {
     const int grid = scan_grid(m, kInsertCtasPerSm);
-    const int64_t budget = room / ((int64_t)grid * kThreads);
-    NVTB_CUDA_OK(cudaFuncSetAttribute(insert_keys_kernel<KeyT>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kInsertSmemBytes));
-    insert_keys_kernel<KeyT><<<grid, kThreads, kInsertSmemBytes, st>>>(kp, mp, m, h->t, h->ctr,
-                                                                        h->arena, budget);
+    const int64_t budget = 0;
+    constexpr int kSmemBytes = SmemAgg<KeyT>::kBytes;
+    if (h->t.narrow) {
+      NVTB_CUDA_OK(cudaFuncSetAttribute(insert_keys_kernel<KeyT, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      insert_keys_kernel<KeyT, true><<<grid, kThreads, kSmemBytes, st>>>(kp, mp, m, h->t, h->ctr, h->arena, budget);
+    } else {
+      NVTB_CUDA_OK(cudaFuncSetAttribute(insert_keys_kernel<KeyT, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      insert_keys_kernel<KeyT, false><<<grid, kThreads, kSmemBytes, st>>>(kp, mp, m, h->t, h->ctr, h->arena, budget);
+    }
   } else {
     const int grid = plain_grid(m);
-    const int64_t budget = room / ((int64_t)grid * kThreads);
+    const int64_t budget = 0;
     insert_agg_kernel<KeyT><<<grid, kThreads, 0, st>>>(kp, mp, ac, m, h->t, h->ctr,
                                                        h->special_vals, h->arena, budget);
   }
@@ -825,7 +1032,7 @@ int nvtb_hashagg_create(nvtb_hashagg_t** out, int n_agg, int64_t capacity_hint) 
   h->n_agg = n_agg;
   h->hint = capacity_hint > 0 ? capacity_hint : 0;
   cudaStream_t st = 0;
-  int rc = table_alloc(&h->t, next_pow2(std::max<int64_t>((int64_t)(2.5 * capacity_hint), kMinCapacity)), n_agg, st);
+  int rc = table_alloc(&h->t, next_pow2(std::max<int64_t>((int64_t)(2.5 * capacity_hint), kMinCapacity)), n_agg, false, st);
   if (rc) { delete h; return rc; }
   NVTB_CUDA_OK(cudaMalloc(&h->ctr, sizeof(Counters)));
   NVTB_CUDA_OK(cudaMalloc(&h->special_vals, sizeof(double) * 8 * (n_agg > 0 ? n_agg : 1)));
@@ -887,6 +1094,23 @@ int nvtb_hashagg_insert(nvtb_hashagg_t* h, const nvtb_col_t* key,
     ac.data[j] = agg_cols[j].data; ac.mask[j] = agg_cols[j].validity; ac.dtype[j] = agg_cols[j].dtype;
   }
   const size_t ksz = dtype_size(key->dtype);
+  {
+    int rc = settle(h);
+    if (rc) return rc;
+    const bool can_narrow = h->n_agg == 0 && key->dtype == NVTB_I32 &&
+                            h->rows_total + n < (int64_t)0xFFFFFFF0ll;
+    if (h->rows_total == 0 && h->u_known == 0 && can_narrow && !h->t.narrow) {
+      // empty table: switch to the 8-byte layout in place
+      const int64_t cap = h->t.capacity;
+      rc = table_free(&h->t, st);
+      if (rc) return rc;
+      rc = table_alloc(&h->t, cap, 0, true, st);
+      if (rc) return rc;
+    } else if (h->t.narrow && !can_narrow) {
+      rc = grow_to(h, h->t.capacity, st, /*force_wide=*/true);   // int64 keys or >= 2^32 rows
+      if (rc) return rc;
+    }
+  }
   // batches: [sample of 2^20 rows when nothing is known about the cardinality] + the rest
   int64_t off = 0;
   while (off < n) {
@@ -922,12 +1146,12 @@ int nvtb_hashagg_merge(nvtb_hashagg_t* h, const int64_t* keys,
   cudaStream_t st = (cudaStream_t)stream;
   int rc = settle(h);
   if (rc) return rc;
-  // pre-aggregated rows: distinct keys within the batch => every row may be new
-  rc = grow_to(h, next_pow2((int64_t)(2.5 * (double)(h->u_known + n)) + 1), st);
+  // pre-aggregated rows: distinct keys within the batch => every row may be new; sizes are
+  // arbitrary int64 => wide layout
+  rc = grow_to(h, next_pow2((int64_t)(2.5 * (double)(h->u_known + n)) + 1), st, /*force_wide=*/true);
   if (rc) return rc;
   rc = arena_acquire(h, &h->arena, n, h->n_agg);
   if (rc) return rc;
-  NVTB_CUDA_OK(cudaMemsetAsync(&h->ctr->ovf_count, 0, sizeof(unsigned long long), st));
   rc = launch_merge(h, keys, sizes, vals, n, h->arena, st);
   if (rc) return rc;
   h->rows_total += n;

@@ -14,6 +14,7 @@
 // the N-row stream).  The encode is a single in-order probe pass: no join, no
 // sort back to row order.
 #include <algorithm>
+#include <cstddef>
 #include <cub/cub.cuh>
 #include <new>
 
@@ -23,17 +24,62 @@ namespace nvtb {
 
 // read-only lookup table: slot = {key, position}; immutable after build so the
 // probes go through the read-only (L1-cacheable) path.
+// Two slot layouts, like the aggregation table:
+//   wide   (16 B) {int64 key, int64 position}; empty key = INT64_MIN
+//   narrow ( 8 B) ((uint32)(position + 1) << 32) | (uint32)key; empty = 0.  Used when
+//                 every key fits int32 and n < 2^31: half the footprint, so more of
+//                 the table stays in L1/L2, and one 8-byte load per probe.
 struct Lookup {
-  int64_t* slots;     // [2*capacity]
+  int64_t* slots;     // wide: [2*capacity]; narrow: [capacity]
   int64_t capacity;   // power of two, >= 2 * n
   int64_t min_key_pos;  // position of key INT64_MIN (the EMPTY sentinel) or -1
+  int narrow;
 };
 
-__global__ void lookup_init_kernel(int64_t* slots, int64_t capacity) {
+__global__ void lookup_init_kernel(int64_t* slots, int64_t capacity, int narrow) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < capacity; s += stride) {
+    if (narrow) { slots[s] = 0; continue; }
     slots[2 * s] = kEmptyKey;
     slots[2 * s + 1] = INT64_MAX;
+  }
+}
+
+// all keys within int32?  (decides the narrow layout)
+__global__ void keys_fit_i32_kernel(const int64_t* __restrict__ keys, int64_t n, int* flag) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t k = keys[i];
+    bad = bad || (k < (int64_t)INT32_MIN) || (k > (int64_t)INT32_MAX);
+  }
+  if (bad) *flag = 0;
+}
+
+// narrow build: keys are distinct int32 values.  A repeated key (user vocab) keeps the
+// smallest position: atomicMax on the packed word would order by position+1 in the high
+// half, so the first position wins through an explicit compare-and-swap loop.
+__global__ void lookup_build_narrow_kernel(const int64_t* __restrict__ keys, int64_t n,
+                                           unsigned long long* slots, int64_t capacity) {
+  const int64_t mask = capacity - 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned key = (unsigned)(int)keys[i];
+    const unsigned long long want = ((unsigned long long)(unsigned)(i + 1) << 32) | key;
+    int64_t slot = (int64_t)(table_mix64((uint64_t)(int64_t)(int)key) & (uint64_t)mask);
+    while (true) {
+      unsigned long long prev = atomicCAS(slots + slot, 0ull, want);
+      if (prev == 0ull) break;
+      if ((unsigned)prev == key) {
+        while ((prev >> 32) > (unsigned long long)(i + 1)) {   // keep the smallest position
+          const unsigned long long seen = atomicCAS(slots + slot, prev, want);
+          if (seen == prev) break;
+          prev = seen;
+        }
+        break;
+      }
+      slot = (slot + 1) & mask;
+    }
   }
 }
 
@@ -62,16 +108,60 @@ __global__ void lookup_build_kernel(const int64_t* __restrict__ keys, int64_t n,
   }
 }
 
-__device__ __forceinline__ int64_t lookup_find(const Lookup& t, int64_t key) {
-  if (key == kEmptyKey) return t.min_key_pos;
-  const int64_t mask = t.capacity - 1;
-  int64_t slot = (int64_t)(table_mix64((uint64_t)key) & (uint64_t)mask);
-  while (true) {
+__device__ __forceinline__ int64_t lookup_first_slot(const Lookup& t, int64_t key) {
+  return (int64_t)(table_mix64((uint64_t)key) & (uint64_t)(t.capacity - 1));
+}
+
+struct SlotKV { long long k, v; };
+
+template <bool NARROW>
+__device__ __forceinline__ SlotKV lookup_load(const Lookup& t, int64_t slot) {
+  SlotKV r;
+  if (NARROW) {
+    const unsigned long long w = __ldg(reinterpret_cast<const unsigned long long*>(t.slots) + slot);
+    r.k = (long long)w;      // packed word (0 = empty)
+    r.v = 0;
+  } else {
     const longlong2 kv = __ldg(reinterpret_cast<const longlong2*>(t.slots + 2 * slot));
-    if (kv.x == key) return kv.y;
-    if (kv.x == kEmptyKey) return -1;
-    slot = (slot + 1) & mask;
+    r.k = kv.x; r.v = kv.y;
   }
+  return r;
+}
+
+// position of `key` or -1, starting from a prefetched first probe.  Single exit:
+// the lanes of a warp iterate together (load factor <= 0.5 => ~1.5 probes).
+template <bool NARROW>
+__device__ __forceinline__ int64_t lookup_resolve(const Lookup& t, int64_t key, int64_t slot, SlotKV kv) {
+  if (!NARROW && key == kEmptyKey) return t.min_key_pos;
+  const int64_t mask = t.capacity - 1;
+  int64_t pos = -1;
+  bool done = false;
+#pragma unroll 1
+  while (!done) {
+    if (NARROW) {
+      const unsigned long long w = (unsigned long long)kv.k;
+      if (w == 0ull) done = true;
+      else if ((unsigned)w == (unsigned)key) { pos = (int64_t)(w >> 32) - 1; done = true; }
+    } else {
+      if (kv.k == key) { pos = kv.v; done = true; }
+      else if (kv.k == kEmptyKey) done = true;
+    }
+    if (!done) {
+      slot = (slot + 1) & mask;
+      kv = lookup_load<NARROW>(t, slot);
+    }
+  }
+  return pos;
+}
+
+__device__ __forceinline__ int64_t lookup_find(const Lookup& t, int64_t key) {
+  if (t.narrow) {
+    if (key < (int64_t)INT32_MIN || key > (int64_t)INT32_MAX) return -1;
+    const int64_t s = lookup_first_slot(t, key);
+    return lookup_resolve<true>(t, key, s, lookup_load<true>(t, s));
+  }
+  const int64_t s = lookup_first_slot(t, key);
+  return lookup_resolve<false>(t, key, s, lookup_load<false>(t, s));
 }
 
 // number of leading rows with size >= threshold in a size-descending array
@@ -120,26 +210,68 @@ struct EncodeParams {
   uint64_t num_buckets;  // <= 1: single OOV index
 };
 
-template <typename KeyT, typename OutT>
+template <typename KeyT, typename OutT, bool NARROW>
 __global__ void __launch_bounds__(kThreads)
 encode_kernel(const KeyT* __restrict__ keys, const uint8_t* __restrict__ mask,
               int64_t n, Lookup t, EncodeParams p, HashCols hc,
               OutT* __restrict__ out) {
   const bool aligned = is_aligned32(keys) && is_aligned32(out);
-  map_rows<KeyT, OutT>(keys, mask, out, n, aligned,
-                       [&](int64_t i, KeyT x, bool valid) -> OutT {
-                         if (!valid) return (OutT)p.null_label;
-                         const int64_t pos = lookup_find(t, (int64_t)x);
-                         if (pos >= 0) return (OutT)(p.first_label + pos);
-                         int64_t lab = p.oov_label;
-                         if (p.num_buckets > 1) {
-                           const uint64_t h = hc.ncols > 0
-                                                  ? hash_cols_at(hc, i)
-                                                  : pandas_mix64(value_bits<KeyT>(x));
-                           lab += (int64_t)(h % p.num_buckets);
-                         }
-                         return (OutT)lab;
-                       });
+  auto in_range = [](long long k) -> bool {
+    return !NARROW || (k >= (long long)INT32_MIN && k <= (long long)INT32_MAX);
+  };
+  auto label_of = [&](int64_t i, KeyT x, bool valid, int64_t pos) -> OutT {
+    if (!valid) return (OutT)p.null_label;
+    if (pos >= 0) return (OutT)(p.first_label + pos);
+    int64_t lab = p.oov_label;
+    if (p.num_buckets > 1) {
+      const uint64_t h = hc.ncols > 0 ? hash_cols_at(hc, i) : pandas_mix64(value_bits<KeyT>(x));
+      lab += (int64_t)(h % p.num_buckets);
+    }
+    return (OutT)lab;
+  };
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * kTile;
+    if (aligned && base + kTile <= n) {
+      KeyT v[kGroups][kRows];
+      unsigned m[kGroups];
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        const int64_t i = base + (int64_t)g * (kThreads * kRows) + (int64_t)threadIdx.x * kRows;
+        ld_rows8<KeyT>(keys + i, v[g]);
+        m[g] = valid8(mask, i);
+      }
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        const int64_t i = base + (int64_t)g * (kThreads * kRows) + (int64_t)threadIdx.x * kRows;
+        // (1) first-probe loads of all 8 keys back to back, (2) resolve, (3) one 256-bit store
+        int64_t slot[kRows];
+        SlotKV kv[kRows];
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+          slot[k] = lookup_first_slot(t, (long long)v[g][k]);
+          kv[k] = lookup_load<NARROW>(t, slot[k]);
+        }
+        OutT o[kRows];
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+          const bool valid = (m[g] >> k) & 1u;
+          const long long key = (long long)v[g][k];
+          int64_t pos = -1;
+          if (valid && in_range(key)) pos = lookup_resolve<NARROW>(t, key, slot[k], kv[k]);
+          o[k] = label_of(i + k, v[g][k], valid, pos);
+        }
+        st_rows8<OutT>(out + i, o);
+      }
+    } else {
+      const int64_t end = (base + kTile < n) ? base + kTile : n;
+      for (int64_t i = base + threadIdx.x; i < end; i += kThreads) {
+        const bool valid = valid1(mask, i);
+        const KeyT x = keys[i];
+        out[i] = label_of(i, x, valid, valid ? lookup_find(t, (int64_t)x) : -1);
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -180,29 +312,134 @@ static int64_t pow2_at_least(int64_t v) {
   return p;
 }
 
-static int lookup_create(Lookup* t, const int64_t* keys, int64_t n, bool may_have_dups,
-                         cudaStream_t st) {
+struct VocabScalars {
+  long long n_keep;
+  long long sum_kept;
+  long long sum_all;
+  int fit_i32;             // 1 while every kept key fits int32
+  long long min_key_pos;   // position of the INT64_MIN key, or -1
+};
+
+// sums of the kept / all sizes, and "do the kept keys fit int32?"
+__global__ void __launch_bounds__(kThreads)
+vocab_scalars_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes,
+                     int64_t n, int64_t n_keep, VocabScalars* sc) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  long long kept = 0, all = 0;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long sz = sizes[i];
+    all += sz;
+    if (i < n_keep) {
+      kept += sz;
+      const int64_t k = keys[i];
+      bad = bad || (k < (int64_t)INT32_MIN) || (k > (int64_t)INT32_MAX);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kept += __shfl_down_sync(0xffffffffu, kept, o);
+    all += __shfl_down_sync(0xffffffffu, all, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (kept) atomicAdd(reinterpret_cast<unsigned long long*>(&sc->sum_kept), (unsigned long long)kept);
+    if (all) atomicAdd(reinterpret_cast<unsigned long long*>(&sc->sum_all), (unsigned long long)all);
+  }
+  if (bad) sc->fit_i32 = 0;
+}
+
+// build either layout; which one is decided by a DEVICE flag so no host sync is needed
+__global__ void __launch_bounds__(kThreads)
+lookup_build_any_kernel(const int64_t* __restrict__ keys, int64_t n, int64_t* slots,
+                        int64_t capacity, const int* fit_i32, long long* min_key_pos) {
+  const bool narrow = (fit_i32 != nullptr) && (*fit_i32 != 0);
+  const int64_t mask = capacity - 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long* ns = reinterpret_cast<unsigned long long*>(slots);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long k = keys[i];
+    if (narrow) {
+      const unsigned key = (unsigned)(int)k;
+      const unsigned long long want = ((unsigned long long)(unsigned)(i + 1) << 32) | key;
+      int64_t slot = (int64_t)(table_mix64((uint64_t)k) & (uint64_t)mask);
+      while (true) {
+        unsigned long long prev = atomicCAS(ns + slot, 0ull, want);
+        if (prev == 0ull) break;
+        if ((unsigned)prev == key) {
+          while ((prev >> 32) > (unsigned long long)(i + 1)) {   // keep the smallest position
+            const unsigned long long seen = atomicCAS(ns + slot, prev, want);
+            if (seen == prev) break;
+            prev = seen;
+          }
+          break;
+        }
+        slot = (slot + 1) & mask;
+      }
+    } else {
+      if (k == kEmptyKey) { *min_key_pos = i; continue; }
+      int64_t slot = (int64_t)(table_mix64((uint64_t)k) & (uint64_t)mask);
+      while (true) {
+        long long prev = (long long)atomicCAS(reinterpret_cast<unsigned long long*>(slots + 2 * slot),
+                                              (unsigned long long)kEmptyKey, (unsigned long long)k);
+        if (prev == kEmptyKey || prev == k) {
+          atomicMin(reinterpret_cast<long long*>(slots + 2 * slot + 1), (long long)i);
+          break;
+        }
+        slot = (slot + 1) & mask;
+      }
+    }
+  }
+}
+
+__global__ void lookup_init_any_kernel(int64_t* slots, int64_t capacity, const int* fit_i32) {
+  const bool narrow = (fit_i32 != nullptr) && (*fit_i32 != 0);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < capacity; s += stride) {
+    if (narrow) {
+      slots[s] = 0;                 // narrow table uses the first `capacity` words only
+    } else {
+      slots[2 * s] = kEmptyKey;
+      slots[2 * s + 1] = INT64_MAX;
+    }
+  }
+}
+
+// Allocates for the wide layout; `fit_i32` (device, may be NULL = wide) selects the
+// layout at kernel run time.  The CALLER sets t->narrow / t->min_key_pos after its sync.
+static int lookup_create(Lookup* t, const int64_t* keys, int64_t n, const int* fit_i32,
+                         cudaStream_t st, long long* d_min_key_pos = nullptr) {
   t->capacity = pow2_at_least(2 * n);
   t->min_key_pos = -1;
   t->slots = nullptr;
+  t->narrow = 0;
   NVTB_CUDA_OK(cudaMallocAsync(&t->slots, sizeof(int64_t) * 2 * t->capacity, st));
   const int g0 = (int)std::min<int64_t>((t->capacity + kThreads - 1) / kThreads, (int64_t)sm_count() * 8);
-  lookup_init_kernel<<<g0, kThreads, 0, st>>>(t->slots, t->capacity);
+  lookup_init_any_kernel<<<g0, kThreads, 0, st>>>(t->slots, t->capacity, fit_i32);
   NVTB_LAUNCH_OK();
   if (n > 0) {
-    long long* d_min = nullptr;
-    NVTB_CUDA_OK(cudaMallocAsync(&d_min, sizeof(long long), st));
-    NVTB_CUDA_OK(cudaMemsetAsync(d_min, 0xFF, sizeof(long long), st));  // -1
-    const int g1 = (int)std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8);
-    lookup_build_kernel<<<g1, kThreads, 0, st>>>(keys, n, t->slots, t->capacity, d_min);
+    const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
+    long long* mk = d_min_key_pos;
+    if (fit_i32 != nullptr && mk == nullptr)
+      mk = const_cast<long long*>(reinterpret_cast<const long long*>(
+          reinterpret_cast<const char*>(fit_i32) - offsetof(VocabScalars, fit_i32) + offsetof(VocabScalars, min_key_pos)));
+    lookup_build_any_kernel<<<g1, kThreads, 0, st>>>(keys, n, t->slots, t->capacity, fit_i32, mk);
     NVTB_LAUNCH_OK();
-    (void)may_have_dups;
-    long long h_min = -1;
-    NVTB_CUDA_OK(cudaMemcpyAsync(&h_min, d_min, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    NVTB_CUDA_OK(cudaStreamSynchronize(st));
-    NVTB_CUDA_OK(cudaFreeAsync(d_min, st));
-    t->min_key_pos = h_min;
   }
+  return NVTB_OK;
+}
+
+// wide-only variant with its own sync (user vocabs, group-stats tables)
+static int lookup_create_wide(Lookup* t, const int64_t* keys, int64_t n, cudaStream_t st) {
+  long long* d_min = nullptr;
+  NVTB_CUDA_OK(cudaMallocAsync(&d_min, sizeof(long long), st));
+  NVTB_CUDA_OK(cudaMemsetAsync(d_min, 0xFF, sizeof(long long), st));  // -1
+  int rc = lookup_create(t, keys, n, nullptr, st, d_min);
+  if (rc) return rc;
+  long long h_min = -1;
+  NVTB_CUDA_OK(cudaMemcpyAsync(&h_min, d_min, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  NVTB_CUDA_OK(cudaStreamSynchronize(st));
+  NVTB_CUDA_OK(cudaFreeAsync(d_min, st));
+  t->min_key_pos = h_min;
   return NVTB_OK;
 }
 
@@ -245,6 +482,7 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* siz
   v->info.n_total = n;
   v->info.null_size = null_size;
   int64_t n_keep = n;
+  VocabScalars* d_sc = nullptr;
   if (n > 0) {
     // (1) key asc, (2) stable size desc  =>  (size desc, key asc)
     int64_t *k1 = nullptr, *s1 = nullptr, *k2 = nullptr, *s2 = nullptr;
@@ -262,53 +500,48 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* siz
     NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, s1, s2, k1, k2, n, 0, 64, st));
     NVTB_CUDA_OK(cudaFreeAsync(k1, st));
     NVTB_CUDA_OK(cudaFreeAsync(s1, st));
+    NVTB_CUDA_OK(cudaFreeAsync(tmp, st));
+    // the sorted arrays ARE the vocabulary (first n_keep rows); no second copy
+    v->keys = k2;
+    v->sizes = s2;
 
-    // cut (categorify.py:766-785)
-    long long* d_scalars = nullptr;  // [0]=n_ge, [1]=sum kept, [2]=sum all
-    NVTB_CUDA_OK(cudaMallocAsync(&d_scalars, sizeof(long long) * 4, st));
-    NVTB_CUDA_OK(cudaMemsetAsync(d_scalars, 0, sizeof(long long) * 4, st));
+    // cut (categorify.py:766-785) + meta sums + int32 check: all on the device, ONE
+    // host sync at the end (two when a freq_threshold makes n_keep data-dependent)
+    NVTB_CUDA_OK(cudaMallocAsync(&d_sc, sizeof(VocabScalars), st));
+    // fit_i32 starts at 1 only if positions fit the 31-bit field of the narrow layout
+    const VocabScalars init = {n, 0, 0, (n < (int64_t)0x7FFFFFF0) ? 1 : 0, -1};
+    NVTB_CUDA_OK(cudaMemcpyAsync(d_sc, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const int g = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
     if (freq_threshold > 0) {
-      const int g = (int)std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8);
-      count_ge_kernel<<<g, kThreads, 0, st>>>(s2, n, freq_threshold, d_scalars);
+      NVTB_CUDA_OK(cudaMemsetAsync(&d_sc->n_keep, 0, sizeof(long long), st));
+      count_ge_kernel<<<g, kThreads, 0, st>>>(s2, n, freq_threshold, &d_sc->n_keep);
       NVTB_LAUNCH_OK();
-      long long n_ge = 0;
-      NVTB_CUDA_OK(cudaMemcpyAsync(&n_ge, d_scalars, sizeof(long long), cudaMemcpyDeviceToHost, st));
+      VocabScalars h;
+      NVTB_CUDA_OK(cudaMemcpyAsync(&h, d_sc, sizeof(h), cudaMemcpyDeviceToHost, st));
       NVTB_CUDA_OK(cudaStreamSynchronize(st));
-      n_keep = n_ge;
+      n_keep = h.n_keep;
     } else if (max_size > 0) {
       n_keep = std::min<int64_t>(n, max_size - (oov_count + 2));
+      NVTB_CUDA_OK(cudaMemcpyAsync(&d_sc->n_keep, &n_keep, sizeof(long long), cudaMemcpyHostToDevice, st));
     }
-    size_t rb = 0;
-    NVTB_CUDA_OK(cub::DeviceReduce::Sum(nullptr, rb, s2, (long long*)nullptr, n, st));
-    if (rb > tmp_bytes) {
-      NVTB_CUDA_OK(cudaFreeAsync(tmp, st));
-      tmp_bytes = rb;
-      NVTB_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes, st));
-    }
-    if (n_keep > 0)
-      NVTB_CUDA_OK(cub::DeviceReduce::Sum(tmp, tmp_bytes, s2, d_scalars + 1, n_keep, st));
-    NVTB_CUDA_OK(cub::DeviceReduce::Sum(tmp, tmp_bytes, s2, d_scalars + 2, n, st));
-    long long sums[2] = {0, 0};
-    NVTB_CUDA_OK(cudaMemcpyAsync(sums, d_scalars + 1, sizeof(long long) * 2, cudaMemcpyDeviceToHost, st));
-    NVTB_CUDA_OK(cudaStreamSynchronize(st));
-    v->info.unique_size = sums[0];
-    v->info.oov_size = sums[1] - sums[0];
-    NVTB_CUDA_OK(cudaFreeAsync(d_scalars, st));
-    NVTB_CUDA_OK(cudaFreeAsync(tmp, st));
-
-    if (n_keep > 0) {
-      NVTB_CUDA_OK(cudaMallocAsync(&v->keys, sizeof(int64_t) * n_keep, st));
-      NVTB_CUDA_OK(cudaMallocAsync(&v->sizes, sizeof(int64_t) * n_keep, st));
-      NVTB_CUDA_OK(cudaMemcpyAsync(v->keys, k2, sizeof(int64_t) * n_keep, cudaMemcpyDeviceToDevice, st));
-      NVTB_CUDA_OK(cudaMemcpyAsync(v->sizes, s2, sizeof(int64_t) * n_keep, cudaMemcpyDeviceToDevice, st));
-    }
-    NVTB_CUDA_OK(cudaFreeAsync(k2, st));
-    NVTB_CUDA_OK(cudaFreeAsync(s2, st));
+    vocab_scalars_kernel<<<g, kThreads, 0, st>>>(k2, s2, n, n_keep, d_sc);
+    NVTB_LAUNCH_OK();
   }
   v->info.n_kept = n_keep;
-  int rc = lookup_create(&v->t, v->keys, n_keep, false, st);
+  int rc = lookup_create(&v->t, v->keys, n_keep, d_sc ? &d_sc->fit_i32 : nullptr, st);
   if (rc) { nvtb_vocab_destroy(v); return rc; }
-  NVTB_CUDA_OK(cudaStreamSynchronize(st));
+  if (d_sc) {
+    VocabScalars h;
+    NVTB_CUDA_OK(cudaMemcpyAsync(&h, d_sc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    NVTB_CUDA_OK(cudaStreamSynchronize(st));
+    NVTB_CUDA_OK(cudaFreeAsync(d_sc, st));
+    v->info.unique_size = h.sum_kept;
+    v->info.oov_size = h.sum_all - h.sum_kept;
+    v->t.narrow = h.fit_i32 ? 1 : 0;   // exactly what the device-side init/build kernels used
+    v->t.min_key_pos = h.min_key_pos;
+  } else {
+    NVTB_CUDA_OK(cudaStreamSynchronize(st));
+  }
   *out = v;
   return NVTB_OK;
 }
@@ -331,9 +564,8 @@ int nvtb_vocab_from_arrays(nvtb_vocab_t** out, const int64_t* keys, const int64_
       NVTB_CUDA_OK(cudaMemcpyAsync(v->sizes, sizes, sizeof(int64_t) * n, cudaMemcpyDeviceToDevice, st));
     }
   }
-  int rc = lookup_create(&v->t, v->keys, n, true, st);
+  int rc = lookup_create_wide(&v->t, v->keys, n, st);
   if (rc) { nvtb_vocab_destroy(v); return rc; }
-  NVTB_CUDA_OK(cudaStreamSynchronize(st));
   *out = v;
   return NVTB_OK;
 }
@@ -391,17 +623,19 @@ int nvtb_encode_apply(const nvtb_vocab_t* v, const nvtb_col_t* key, int64_t n,
   EncodeParams p{null_label, oov_label, first_label, num_buckets};
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = scan_grid(n, 8);
+#define NVTB_ENCODE(KT, OT)                                                                        \
+  do {                                                                                             \
+    if (v->t.narrow)                                                                               \
+      encode_kernel<KT, OT, true><<<grid, kThreads, 0, st>>>((const KT*)key->data, key->validity, n, v->t, p, hc, (OT*)out); \
+    else                                                                                           \
+      encode_kernel<KT, OT, false><<<grid, kThreads, 0, st>>>((const KT*)key->data, key->validity, n, v->t, p, hc, (OT*)out); \
+  } while (0)
   if (key->dtype == NVTB_I32) {
-    if (out_dtype == NVTB_I64)
-      encode_kernel<int32_t, int64_t><<<grid, kThreads, 0, st>>>((const int32_t*)key->data, key->validity, n, v->t, p, hc, (int64_t*)out);
-    else
-      encode_kernel<int32_t, int32_t><<<grid, kThreads, 0, st>>>((const int32_t*)key->data, key->validity, n, v->t, p, hc, (int32_t*)out);
+    if (out_dtype == NVTB_I64) NVTB_ENCODE(int32_t, int64_t); else NVTB_ENCODE(int32_t, int32_t);
   } else {
-    if (out_dtype == NVTB_I64)
-      encode_kernel<int64_t, int64_t><<<grid, kThreads, 0, st>>>((const int64_t*)key->data, key->validity, n, v->t, p, hc, (int64_t*)out);
-    else
-      encode_kernel<int64_t, int32_t><<<grid, kThreads, 0, st>>>((const int64_t*)key->data, key->validity, n, v->t, p, hc, (int32_t*)out);
+    if (out_dtype == NVTB_I64) NVTB_ENCODE(int64_t, int64_t); else NVTB_ENCODE(int64_t, int32_t);
   }
+#undef NVTB_ENCODE
   NVTB_LAUNCH_OK();
   return NVTB_OK;
 }
@@ -422,9 +656,8 @@ int nvtb_groupstats_create(nvtb_groupstats_t** out, const int64_t* keys, int64_t
     NVTB_CUDA_OK(cudaMallocAsync(&g->stats, sizeof(double) * n_rows * width, st));
     NVTB_CUDA_OK(cudaMemcpyAsync(g->stats, stats, sizeof(double) * n_rows * width, cudaMemcpyDeviceToDevice, st));
   }
-  int rc = lookup_create(&g->t, keys, n_groups, false, st);
+  int rc = lookup_create_wide(&g->t, keys, n_groups, st);
   if (rc) { nvtb_groupstats_destroy(g); return rc; }
-  NVTB_CUDA_OK(cudaStreamSynchronize(st));
   *out = g;
   return NVTB_OK;
 }

@@ -16,6 +16,16 @@ from .column import Column, DeviceFrame
 from .graph import ColumnSchema, Schema
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev, which=0):
+    key = (dev.index, which)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
+
+
 def _schema_of(frame: DeviceFrame) -> Schema:
     cols = []
     for name, c in frame.items():
@@ -64,6 +74,9 @@ class Dataset:
                  part_size=None, schema: Optional[Schema] = None, device=None,
                  _transform: Optional[Callable] = None, base_dataset=None, **kwargs):
         self._device = device
+        self.cache_on_device = kwargs.pop("cache_on_device", True)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
         self._transform = _transform
         self.base_dataset = base_dataset or self
         self.cpu = cpu     # accepted for API compatibility; there is no CPU engine
@@ -109,10 +122,79 @@ class Dataset:
         return [DeviceFrame.from_pandas(h.reset_index(drop=True), self._device) for h in host]
 
     def partitions(self) -> Iterable[DeviceFrame]:
+        """Device-resident partitions, in order.  Partitions that live in (pinned) host
+        memory are uploaded on a side stream ONE PARTITION AHEAD of the consumer, so the
+        H2D copy of partition i+1 overlaps the kernels working on partition i; uploaded
+        partitions stay cached in HBM (a later pass — transform after fit — does not pay
+        the copy again) unless `cache_on_device=False`."""
         if self._parts is None:
             self._parts = self._ingest()
-        for p in self._parts:
+        parts = self._parts
+        if not any(p.is_host for p in parts) or not torch.cuda.is_available():
+            for p in parts:
+                yield self._transform(p) if self._transform is not None else p
+            return
+        dev = torch.device("cuda", torch.cuda.current_device())
+        copy_stream = _copy_stream(dev)
+        main = torch.cuda.current_stream(dev)
+        pending = {}
+
+        def upload(i):
+            if i < len(parts) and parts[i].is_host and i not in pending:
+                with torch.cuda.stream(copy_stream):
+                    d = parts[i].to(dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                self.h2d_bytes += parts[i].nbytes()
+                pending[i] = (d, ev)
+
+        upload(0)
+        for i in range(len(parts)):
+            upload(i + 1)
+            if i in pending:
+                d, ev = pending.pop(i)
+                main.wait_event(ev)
+                for c in d._cols.values():          # the consumer stream now owns the buffers
+                    c.data.record_stream(main)
+                    if c.validity is not None:
+                        c.validity.record_stream(main)
+                if self.cache_on_device:
+                    parts[i] = d
+                p = d
+            else:
+                p = parts[i]
             yield self._transform(p) if self._transform is not None else p
+
+    def to_host(self, out: Optional[List[DeviceFrame]] = None) -> List[DeviceFrame]:
+        """Materialise every (lazily transformed) partition into pinned host memory.  The
+        D2H copy of partition i runs on a side stream while partition i+1 is computed."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        out_stream = _copy_stream(dev, 1)
+        main = torch.cuda.current_stream(dev)
+        res: List[DeviceFrame] = []
+        for i, part in enumerate(self.partitions()):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            host = out[i] if out is not None and i < len(out) else None
+            cols = {}
+            with torch.cuda.stream(out_stream):
+                out_stream.wait_event(ev)
+                for name, c in part.items():
+                    hb = host[name].data if host is not None and name in host and \
+                        host[name].data.shape == c.data.shape and host[name].data.dtype == c.data.dtype else \
+                        torch.empty(c.data.shape, dtype=c.data.dtype, pin_memory=True)
+                    hb.copy_(c.data, non_blocking=True)
+                    c.data.record_stream(out_stream)
+                    hv = None
+                    if c.validity is not None:
+                        hv = torch.empty(c.validity.shape, dtype=torch.uint8, pin_memory=True)
+                        hv.copy_(c.validity, non_blocking=True)
+                        c.validity.record_stream(out_stream)
+                    cols[name] = Column(hb, hv, c.offsets.cpu() if c.offsets is not None else None)
+                    self.d2h_bytes += hb.numel() * hb.element_size()
+            res.append(DeviceFrame(cols))
+        out_stream.synchronize()
+        return res
 
     @property
     def npartitions(self):

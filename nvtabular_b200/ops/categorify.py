@@ -281,35 +281,49 @@ class Categorify(StatOperator):
         groups = [(s, n) for s, n in self._groups(col_selector) if s not in self.vocabs]
         if not groups:
             return {}
-        parts = list(ddf)   # device-resident partitions (post upstream transforms)
+        it = iter(ddf)
+        first = next(it, None)
+        if first is None:
+            return {storage: self._fit_group(storage, names, []) for storage, names in groups}
+        if self._streamable(first, groups):
+            # numeric keys: ONE streaming pass — partition i is folded into the tables while
+            # partition i+1 is still being uploaded (Dataset.partitions prefetches one ahead)
+            state = {storage: self._open_group(storage, names, first) for storage, names in groups}
+            part = first
+            while part is not None:
+                for storage, names in groups:
+                    space, agg = state[storage]
+                    for n in names:
+                        agg.insert(space.keys_for(part[n]))
+                part = next(it, None)
+            return {storage: self._close_group(storage, [storage], *state[storage]) for storage, names in groups}
+        parts = [first] + list(it)   # strings / general combos need a dictionary pre-pass
         fitted = {}
         for storage, names in groups:
             fitted[storage] = self._fit_group(storage, names, parts)
         return fitted
 
-    def _fit_group(self, storage, names, parts) -> FittedVocab:
-        combo = self.encode_type == "combo" and len(names) > 1
-        if combo:
-            comp_parts = [[_leaf(df[n]) for n in names] for df in parts]
-            if any(c.is_list for df in parts for c in (df[n] for n in names)):
-                raise ValueError("Can't categorical encode multiple list columns")
-            space = ComboKeySpace.fit(comp_parts) if parts else ComboKeySpace([KeySpace("int")] * len(names))
-            key_names = names
-        else:
-            cols_all = [df[n] for df in parts for n in names]
-            space = KeySpace.for_columns([_leaf(c) for c in cols_all]) if cols_all else KeySpace("int", None, np.dtype("int64"))
-            key_names = [storage]
+    def _streamable(self, df, groups) -> bool:
+        for _, names in groups:
+            if self.encode_type == "combo" and len(names) > 1:
+                return False
+            if any(df[n].is_string for n in names):
+                return False
+        return True
+
+    def _get_agg(self, storage):
         agg = self._aggs.get(storage)
         if agg is None:
             agg = self._aggs[storage] = engine.HashAgg(0)
         else:
             agg.reset()
-        for df in parts:
-            if combo:
-                agg.insert(space.keys_for([df[n] for n in names]))
-            else:
-                for n in names:          # joint encoding: every column feeds the SAME table
-                    agg.insert(space.keys_for(df[n]))
+        return agg
+
+    def _open_group(self, storage, names, df):
+        space = KeySpace.for_columns([_leaf(df[n]) for n in names])
+        return space, self._get_agg(storage)
+
+    def _close_group(self, storage, key_names, space, agg) -> FittedVocab:
         keys, sizes, null_size = _global_unique_merge(agg)
         ft = _resolve(self.freq_threshold, storage, 0) or 0
         ms = _resolve(self.max_size, storage, 0) or 0
@@ -331,6 +345,27 @@ class Categorify(StatOperator):
                               f"This is large compared to the suggested upper limit of {limit} bytes!"
                               f"(12.5% of the total memory by default)")
         return FittedVocab(storage, key_names, space, vocab, nb)
+
+    def _fit_group(self, storage, names, parts) -> FittedVocab:
+        combo = self.encode_type == "combo" and len(names) > 1
+        if combo:
+            comp_parts = [[_leaf(df[n]) for n in names] for df in parts]
+            if any(c.is_list for df in parts for c in (df[n] for n in names)):
+                raise ValueError("Can't categorical encode multiple list columns")
+            space = ComboKeySpace.fit(comp_parts) if parts else ComboKeySpace([KeySpace("int")] * len(names))
+            key_names = names
+        else:
+            cols_all = [df[n] for df in parts for n in names]
+            space = KeySpace.for_columns([_leaf(c) for c in cols_all]) if cols_all else KeySpace("int", None, np.dtype("int64"))
+            key_names = [storage]
+        agg = self._get_agg(storage)
+        for df in parts:
+            if combo:
+                agg.insert(space.keys_for([df[n] for n in names]))
+            else:
+                for n in names:          # joint encoding: every column feeds the SAME table
+                    agg.insert(space.keys_for(df[n]))
+        return self._close_group(storage, key_names, space, agg)
 
     def fit_finalize(self, categories):
         base = os.path.join(self.out_path, "categories")

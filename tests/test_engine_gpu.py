@@ -224,6 +224,27 @@ def test_hashagg_growth_and_batches(eng):
     _agg_check(eng, arr, None, batches=3)
 
 
+def test_hashagg_adversarial_order_uses_arena(eng):
+    """The table is sized from the first 2^20 rows; here they are all ONE key and the
+    remaining rows are all distinct, so the estimate is maximally wrong: almost every
+    pair is refused into the overflow arena and folded back in by settle().  Results
+    must still be exact."""
+    n_head, n_tail = (1 << 20) + 4096, 6_000_000
+    arr = np.concatenate([np.full(n_head, 7, dtype="int32"),
+                          (np.arange(n_tail, dtype="int64") * 2654435761 % (1 << 31)).astype("int32")])
+    _agg_check(eng, arr, None)
+    # same through a reused (reset) handle and a second, differently ordered batch
+    from nvtabular_b200.column import Column
+    h = eng.HashAgg(0)
+    for _ in range(2):
+        h.reset()
+        h.insert(_col(arr))
+        h.insert(_col(arr[::-1].copy()))
+        keys, sizes, _, ns, _ = h.export()
+        assert int(sizes.sum().item()) == 2 * len(arr) and ns == 0
+        assert keys.numel() == len(np.unique(arr))
+
+
 def test_hashagg_skewed_zipf(eng):
     rng = np.random.default_rng(7)
     n = 3_000_000

@@ -506,3 +506,68 @@ def test_criteo_shape_workflow_vs_oracle(nvt, ops, tmp_path):
     exp2 = o.transform(pd.DataFrame({c: df2[c].astype("float64") for c in cats}))
     for c in cats:
         np.testing.assert_array_equal(out2[c].to_numpy(), exp2[c].to_numpy())
+
+
+def test_full_size_properties(nvt, ops, tmp_path):
+    """Size-independent properties at a bench-scale table (2^24 rows x 39 columns), where the
+    CPU oracle would take minutes: meta counts add up to the row count, labels stay inside
+    [1, cardinality), nulls map to 1, fit is idempotent (second fit == first), transform of the
+    kept keys is a bijection onto [first_label, first_label + n_kept), normalised columns have
+    mean 0 / std 1, and a 1/64 sample agrees bit-exactly with the oracle run on that sample's
+    rows against the same vocabulary."""
+    import torch
+    from nvtabular_b200.column import unpack_validity
+    from nvtabular_b200.synth import CAT_NAMES, CONT_NAMES, criteo_frame
+    rows = 1 << 24
+    frame = criteo_frame(rows, total_rows=rows, device="cuda")
+    cats = CAT_NAMES >> ops.Categorify(out_path=str(tmp_path))
+    conts = CONT_NAMES >> ops.FillMissing() >> ops.Normalize()
+    wf = nvt.Workflow(cats + conts + ["label"])
+    ds = nvt.Dataset(frame)
+    wf.fit(ds)
+    out = next(iter(wf.transform(ds).partitions()))
+    cat_op = cats.op
+    first = {}
+    for c in CAT_NAMES:
+        fv = cat_op.categories.fitted[c]
+        v = fv.vocab
+        col = frame[c]
+        nulls = rows - int(unpack_validity(col.validity, rows).sum().item()) if col.validity is not None else 0
+        assert v.null_size == nulls
+        assert v.null_size + v.oov_size + v.unique_size == rows       # num_observed sums to len(df)
+        lab = out[c].data
+        assert lab.dtype == torch.int64 and int(lab.min()) >= 1 and int(lab.max()) == 2 + v.n_kept
+        if col.validity is not None:
+            assert bool((lab[~unpack_validity(col.validity, rows)] == 1).all())
+        # every kept key encodes to its own position: a bijection onto [3, 3 + n_kept)
+        keys, sizes = v.export()
+        kc = nvt.Column(keys.to(torch.int32))
+        enc = v.encode(kc, 1, 2, 3)
+        assert torch.equal(enc, torch.arange(3, 3 + v.n_kept, device="cuda"))
+        # (size desc, key asc)
+        assert bool((sizes[:-1] >= sizes[1:]).all())
+        ties = sizes[:-1] == sizes[1:]
+        assert bool((keys[:-1][ties] < keys[1:][ties]).all())
+        first[c] = (keys.clone(), sizes.clone())
+    for c in CONT_NAMES:
+        x = out[c].data
+        assert x.dtype == torch.float64 and abs(float(x.mean())) < 1e-9 and abs(float(x.std()) - 1) < 1e-6
+    # idempotence: a second fit over the same data reproduces the vocabularies exactly
+    wf.fit(ds)
+    for c in CAT_NAMES:
+        keys, sizes = cat_op.categories.fitted[c].vocab.export()
+        assert torch.equal(keys, first[c][0]) and torch.equal(sizes, first[c][1])
+    # 1/64 sample vs the oracle's encode against the SAME vocabulary
+    from oracle.categorify import Vocab as OVocab, categorify_encode
+    idx = torch.arange(0, rows, 64, device="cuda")
+    for c in ["C1", "C6", "C20", "C23"]:
+        keys, sizes = first[c]
+        uniq = pd.DataFrame({c: keys.cpu().numpy(), f"{c}_size": sizes.cpu().numpy()})
+        uniq.index = pd.RangeIndex(3, 3 + len(uniq))
+        ov = OVocab(c, [c], uniq, pd.DataFrame())
+        vals = frame[c].data[idx].cpu().numpy()
+        valid = unpack_validity(frame[c].validity, rows)[idx].cpu().numpy() if frame[c].validity is not None \
+            else np.ones(len(vals), bool)
+        exp = categorify_encode(pd.DataFrame({c: vals}), c, ov)
+        exp[~valid] = 1
+        np.testing.assert_array_equal(out[c].data[idx].cpu().numpy(), exp)
