@@ -23,6 +23,9 @@ namespace nvtb {
 // ---------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int sm_count();
+// keep stream-ordered frees cached in the device's default memory pool instead of
+// returning them to the OS at every synchronisation (the CUDA default)
+void ensure_pool_configured();
 
 #define NVTB_CUDA_OK(expr)                                                    \
   do {                                                                        \

@@ -124,107 +124,132 @@ __device__ __forceinline__ void vals_combine(double* __restrict__ dst,
   if (mx == mx) atomicMax(reinterpret_cast<long long*>(dst + 3), (long long)enc_ordered(mx));
 }
 
-template <bool NARROW>
-__device__ __forceinline__ unsigned long long slot_load(const Table& t, int64_t slot) {
-  const unsigned long long* p = reinterpret_cast<const unsigned long long*>(t.slots) + (NARROW ? slot : 2 * slot);
-  return __ldcg(p);
-}
-
 // append one refused pair (rare path: a plain atomic, safe under any divergence)
 __device__ __forceinline__ int64_t arena_claim(Counters* ctr) {
   return (int64_t)atomicAdd(&ctr->ovf_count, 1ull);
 }
 
-// Fold (key, add) into the table starting from a PREFETCHED first probe
-// (`slot`, `word`): callers issue the first-probe loads of several keys back to
-// back and only then resolve them, so a thread keeps up to 8 table reads in
-// flight.  The common case (first probe finds the key) is a handful of inlined
-// instructions; everything else (claiming a new key, walking the probe sequence)
-// lives in ONE out-of-line copy so the kernel stays small enough for the
-// instruction cache even though 16 rows are unrolled per thread.
-// Returns the slot, or -1 when kMaxProbes slots were inspected (pair refused).
-// There is no load-factor guard: a table that is too small simply fills up, probes
-// start failing, refused pairs go to the arena and settle() regrows the table.
+// A probe = the table words fetched for one key.
+//   narrow: one 32-byte SECTOR = a 4-way bucket of packed slots, fetched with a single
+//           256-bit load (LDG.E.256).  A key displaced by collisions is still found on
+//           the inlined fast path unless its bucket holds > 4 keys; with one slot per
+//           probe ~load% of ALL rows took the divergent out-of-line path.
+//   wide:   one 16-byte slot (key word only), linear probing.
+template <bool NARROW> struct Probe;
+template <> struct Probe<true>  { int64_t b; unsigned long long w[4]; };
+template <> struct Probe<false> { int64_t b; unsigned long long w[1]; };
+
+template <bool NARROW>
+__device__ __forceinline__ void probe_load(const Table& t, int64_t b, Probe<NARROW>& p) {
+  p.b = b;
+  if constexpr (NARROW) {
+    const unsigned long long* a = reinterpret_cast<const unsigned long long*>(t.slots) + 4 * b;
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(p.w[0]), "=l"(p.w[1]), "=l"(p.w[2]), "=l"(p.w[3]) : "l"(a));
+  } else {
+    p.w[0] = __ldcg(reinterpret_cast<const unsigned long long*>(t.slots) + 2 * b);
+  }
+}
+
+template <bool NARROW>
+__device__ __forceinline__ int64_t probe_home(const Table& t, int64_t key) {
+  const uint64_t h = table_mix64((uint64_t)key);
+  return NARROW ? (int64_t)(h & (uint64_t)((t.capacity >> 2) - 1)) : (int64_t)(h & (uint64_t)(t.capacity - 1));
+}
+
+template <bool NARROW>
+__device__ __forceinline__ void probe_first(const Table& t, int64_t key, Probe<NARROW>& p) {
+  probe_load<NARROW>(t, probe_home<NARROW>(t, key), p);
+}
+
+// Everything that is not "the key sits in the prefetched bucket": claim an empty slot
+// (64-bit CAS; on the narrow layout the CAS also deposits the count), walk to the next
+// bucket, give up after kMaxProbes buckets (-> -1, the pair is refused).  ONE out-of-line
+// copy keeps the 16-row-unrolled kernel small enough for the instruction cache.
+// There is no load-factor guard: a table that is too small simply fills up, probes start
+// failing, refused pairs go to the arena and settle() regrows the table.
 template <bool NARROW>
 __device__ __noinline__ int64_t upsert_slow(const Table& t, int64_t key, int64_t add,
-                                            int64_t slot, unsigned long long word, unsigned& n_new) {
-  const int64_t mask = t.capacity - 1;
+                                            Probe<NARROW> p, unsigned& n_new) {
   unsigned long long* base = reinterpret_cast<unsigned long long*>(t.slots);
+  const int64_t mask = NARROW ? (t.capacity >> 2) - 1 : t.capacity - 1;
   int64_t result = -1;
   bool done = false;
 #pragma unroll 1
   for (int probe = 0; probe < kMaxProbes && !done; ++probe) {
-    if (NARROW) {
-      bool match = (word != 0ull) && ((unsigned)word == (unsigned)key);
-      if (word == 0ull) {
-        const unsigned long long want =
-            ((unsigned long long)(unsigned)add << 32) | (unsigned long long)(unsigned)key;
-        const unsigned long long prev = atomicCAS(base + slot, 0ull, want);
-        if (prev == 0ull) { ++n_new; result = slot; done = true; }   // the CAS deposited the count
-        else match = ((unsigned)prev == (unsigned)key);              // lost the race, maybe to the same key
-      }
-      if (match && !done) {
-        atomicAdd(reinterpret_cast<unsigned*>(base + slot) + 1, (unsigned)add);
-        result = slot; done = true;
+    if constexpr (NARROW) {
+      const unsigned long long want =
+          ((unsigned long long)(unsigned)add << 32) | (unsigned long long)(unsigned)key;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!done) {
+          unsigned long long cur = p.w[j];
+          if (cur == 0ull) {
+            cur = atomicCAS(base + 4 * p.b + j, 0ull, want);
+            if (cur == 0ull) { ++n_new; result = 4 * p.b + j; done = true; }   // count deposited
+          }
+          if (!done && (unsigned)cur == (unsigned)key) {        // cur != 0 here
+            atomicAdd(reinterpret_cast<unsigned*>(base + 4 * p.b + j) + 1, (unsigned)add);
+            result = 4 * p.b + j; done = true;
+          }
+        }
       }
     } else {
-      bool match = ((long long)word == key);
-      if ((long long)word == kEmptyKey) {
-        const unsigned long long prev = atomicCAS(base + 2 * slot, (unsigned long long)kEmptyKey,
+      bool match = ((long long)p.w[0] == key);
+      if ((long long)p.w[0] == kEmptyKey) {
+        const unsigned long long prev = atomicCAS(base + 2 * p.b, (unsigned long long)kEmptyKey,
                                                   (unsigned long long)key);
         if ((long long)prev == kEmptyKey) { ++n_new; match = true; }
         else match = ((long long)prev == key);
       }
-      if (match && !done) {
-        atomicAdd(base + 2 * slot + 1, (unsigned long long)add);
-        result = slot; done = true;
+      if (match) {
+        atomicAdd(base + 2 * p.b + 1, (unsigned long long)add);
+        result = p.b; done = true;
       }
     }
-    if (!done) {
-      slot = (slot + 1) & mask;
-      word = slot_load<NARROW>(t, slot);
-    }
+    if (!done) probe_load<NARROW>(t, (p.b + 1) & mask, p);
   }
   return result;
 }
 
+// Fold (key, add) into the table starting from a PREFETCHED first probe: callers issue
+// the first-probe loads of several keys back to back and only then resolve them, so a
+// thread keeps several table sectors in flight.  Returns the slot, or -1 (refused).
 template <bool NARROW>
-__device__ __forceinline__ int64_t upsert_add(const Table& t, Counters*, int64_t key, int64_t add,
-                                              int64_t slot, unsigned long long word,
-                                              int64_t&, unsigned& n_new) {
+__device__ __forceinline__ int64_t upsert_add(const Table& t, int64_t key, int64_t add,
+                                              const Probe<NARROW>& p, unsigned& n_new) {
   unsigned long long* base = reinterpret_cast<unsigned long long*>(t.slots);
-  if (NARROW) {
-    if (word != 0ull && (unsigned)word == (unsigned)key) {
-      atomicAdd(reinterpret_cast<unsigned*>(base + slot) + 1, (unsigned)add);
-      return slot;
+  if constexpr (NARROW) {
+    int hit = -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (p.w[j] != 0ull && (unsigned)p.w[j] == (unsigned)key) hit = j;
+    if (hit >= 0) {
+      atomicAdd(reinterpret_cast<unsigned*>(base + 4 * p.b + hit) + 1, (unsigned)add);
+      return 4 * p.b + hit;
     }
   } else {
-    if ((long long)word == key) {
-      atomicAdd(base + 2 * slot + 1, (unsigned long long)add);
-      return slot;
+    if ((long long)p.w[0] == key) {
+      atomicAdd(base + 2 * p.b + 1, (unsigned long long)add);
+      return p.b;
     }
   }
-  return upsert_slow<NARROW>(t, key, add, slot, word, n_new);
+  return upsert_slow<NARROW>(t, key, add, p, n_new);
 }
 
-__device__ __forceinline__ int64_t first_slot(const Table& t, int64_t key) {
-  return (int64_t)(table_mix64((uint64_t)key) & (uint64_t)(t.capacity - 1));
-}
-
-// one-key convenience forms (cold paths: merge, flush)
+// one-key convenience form (cold paths: merge, scalar tails)
 template <bool NARROW>
-__device__ __forceinline__ int64_t upsert_one(const Table& t, Counters* ctr, int64_t key, int64_t add,
-                                              int64_t& budget, unsigned& n_new) {
-  const int64_t slot = first_slot(t, key);
-  return upsert_add<NARROW>(t, ctr, key, add, slot, slot_load<NARROW>(t, slot), budget, n_new);
+__device__ __forceinline__ int64_t upsert_one(const Table& t, int64_t key, int64_t add, unsigned& n_new) {
+  Probe<NARROW> p;
+  probe_first<NARROW>(t, key, p);
+  return upsert_add<NARROW>(t, key, add, p, n_new);
 }
 
 template <bool NARROW>
 __device__ __forceinline__ void upsert_or_spill(const Table& t, const Arena& a, Counters* ctr,
-                                                int64_t key, int64_t add, int64_t slot,
-                                                unsigned long long word, int64_t& budget,
+                                                int64_t key, int64_t add, const Probe<NARROW>& p,
                                                 unsigned& n_new) {
-  if (upsert_add<NARROW>(t, ctr, key, add, slot, word, budget, n_new) < 0) {
+  if (upsert_add<NARROW>(t, key, add, p, n_new) < 0) {
     const int64_t o = arena_claim(ctr);
     if (o < a.cap) { a.keys[o] = key; a.sizes[o] = add; }
   }
@@ -273,41 +298,52 @@ __global__ void special_init_kernel(Counters* ctr, double* special_vals, int n_a
 template <typename KeyT> struct SmemAgg;
 
 template <> struct SmemAgg<int32_t> {
-  static constexpr int kSlots = 8192;
+  // 4096 two-way buckets: one 128-bit shared load fetches both candidate slots of a key,
+  // so a key displaced by a collision is still found on the inlined fast path (with
+  // one-slot-per-probe linear probing ~load% of ALL rows took the divergent slow path).
+  static constexpr int kBuckets = 4096;
+  static constexpr int kSlots = 2 * kBuckets;
   static constexpr int kBytes = kSlots * 8;
   unsigned long long* w;
   __device__ __forceinline__ explicit SmemAgg(unsigned char* raw) : w(reinterpret_cast<unsigned long long*>(raw)) {}
   __device__ __forceinline__ void clear() {
     for (int s = threadIdx.x; s < kSlots; s += kThreads) w[s] = 0ull;
   }
-  __device__ __noinline__ bool fold_slow(unsigned key, unsigned s) {
+  // claim one of the two slots of bucket b for `key` (or find it there); false = bucket full
+  static __device__ __noinline__ bool fold_slow(unsigned long long* w, unsigned key, unsigned b) {
     bool done = false;
-#pragma unroll 1
-    for (int p = 0; p < kSmemProbes && !done; ++p) {
-      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&w[s]);
-      if (cur == 0ull) {
-        cur = atomicCAS(&w[s], 0ull, (1ull << 32) | (unsigned long long)key);
-        if (cur == 0ull) done = true;                      // claimed with count 1
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (!done) {
+        unsigned long long* p = w + 2 * b + j;
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(p);
+        if (cur == 0ull) {
+          cur = atomicCAS(p, 0ull, (1ull << 32) | (unsigned long long)key);
+          if (cur == 0ull) done = true;                          // claimed with count 1
+        }
+        if (!done && cur != 0ull && (unsigned)cur == key) {
+          atomicAdd(reinterpret_cast<unsigned*>(p) + 1, 1u);
+          done = true;
+        }
       }
-      if (!done && (unsigned)cur == key && cur != 0ull) {
-        atomicAdd(reinterpret_cast<unsigned*>(&w[s]) + 1, 1u);
-        done = true;
-      }
-      s = (s + 1) & (kSlots - 1);
     }
     return done;
   }
   // fold one key; true = absorbed.  `hits` counts keys that were already present.
   __device__ __forceinline__ bool fold(long long k, uint64_t h, unsigned& hits) {
     const unsigned key = (unsigned)(int)k;
-    const unsigned s = (unsigned)(h >> 40) & (kSlots - 1);   // bits disjoint from the global slot bits
-    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&w[s]);
-    if (cur != 0ull && (unsigned)cur == key) {
-      atomicAdd(reinterpret_cast<unsigned*>(&w[s]) + 1, 1u);
+    const unsigned b = (unsigned)(h >> 40) & (kBuckets - 1);     // bits disjoint from the global slot bits
+    unsigned long long x, y;
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(w + 2 * b);
+    asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(addr));
+    const bool mx = (x != 0ull) && ((unsigned)x == key);
+    const bool my = (y != 0ull) && ((unsigned)y == key);
+    if (mx || my) {
+      atomicAdd(reinterpret_cast<unsigned*>(w + 2 * b + (mx ? 0 : 1)) + 1, 1u);
       hits++;
       return true;
     }
-    return fold_slow(key, s);
+    return fold_slow(w, key, b);
   }
   __device__ __forceinline__ bool get(int s, long long* key, unsigned* cnt) const {
     const unsigned long long cur = w[s];
@@ -327,7 +363,7 @@ template <> struct SmemAgg<int64_t> {
   __device__ __forceinline__ void clear() {
     for (int s = threadIdx.x; s < kSlots; s += kThreads) { keys[s] = kEmptyKey; cnt[s] = 0u; }
   }
-  __device__ __noinline__ bool fold_slow(long long k, unsigned s) {
+  static __device__ __noinline__ bool fold_slow(long long* keys, unsigned* cnt, long long k, unsigned s) {
     bool done = false;
 #pragma unroll 1
     for (int p = 0; p < kSmemProbes && !done; ++p) {
@@ -350,7 +386,7 @@ template <> struct SmemAgg<int64_t> {
       hits++;
       return true;
     }
-    return fold_slow(k, s);
+    return fold_slow(keys, cnt, k, s);
   }
   __device__ __forceinline__ bool get(int s, long long* key, unsigned* c) const {
     *key = keys[s];
@@ -374,7 +410,6 @@ insert_keys_kernel(const KeyT* __restrict__ keys,
   __syncthreads();
 
   unsigned int n_null = 0, n_min = 0, n_new = 0;
-  int64_t budget = 0;
   bool bypass = false;
   const bool aligned = is_aligned32(keys);
 
@@ -394,19 +429,20 @@ insert_keys_kernel(const KeyT* __restrict__ keys,
         if (bypass || !sm.fold(key, table_mix64((uint64_t)key), hits)) pend |= 1u << k;
       }
     }
-    if (pend != 0) {
-      int64_t slot[kRows];
-      unsigned long long word[kRows];
+    // global phase in two halves of 4 keys: 4 sector loads in flight per thread
 #pragma unroll
-      for (int k = 0; k < kRows; ++k)
-        if ((pend >> k) & 1u) {
-          slot[k] = first_slot(t, (long long)v[k]);
-          word[k] = slot_load<NARROW>(t, slot[k]);
-        }
+    for (int half = 0; half < 2; ++half) {
+      const unsigned hp = (pend >> (4 * half)) & 0xFu;
+      if (hp != 0) {
+        Probe<NARROW> pr[4];
 #pragma unroll
-      for (int k = 0; k < kRows; ++k)
-        if ((pend >> k) & 1u)
-          upsert_or_spill<NARROW>(t, arena, ctr, (long long)v[k], 1, slot[k], word[k], budget, n_new);
+        for (int k = 0; k < 4; ++k)
+          if ((hp >> k) & 1u) probe_first<NARROW>(t, (long long)v[4 * half + k], pr[k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if ((hp >> k) & 1u)
+            upsert_or_spill<NARROW>(t, arena, ctr, (long long)v[4 * half + k], 1, pr[k], n_new);
+      }
     }
   };
 
@@ -434,8 +470,9 @@ insert_keys_kernel(const KeyT* __restrict__ keys,
         if (sizeof(KeyT) == 8 && key == kEmptyKey) { n_min++; continue; }
         rows++;
         if (!bypass && sm.fold(key, table_mix64((uint64_t)key), hits)) continue;
-        const int64_t sl = first_slot(t, key);
-        upsert_or_spill<NARROW>(t, arena, ctr, key, 1, sl, slot_load<NARROW>(t, sl), budget, n_new);
+        Probe<NARROW> pr;
+        probe_first<NARROW>(t, key, pr);
+        upsert_or_spill<NARROW>(t, arena, ctr, key, 1, pr, n_new);
       }
     }
     if (first) {
@@ -459,20 +496,15 @@ insert_keys_kernel(const KeyT* __restrict__ keys,
     long long k[4];
     unsigned c[4];
     bool live[4];
-    int64_t slot[4];
-    unsigned long long word[4];
+    Probe<NARROW> pr[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       live[j] = sm.get(s0 + j * kThreads + threadIdx.x, &k[j], &c[j]);
-      if (live[j]) {
-        slot[j] = first_slot(t, k[j]);
-        word[j] = slot_load<NARROW>(t, slot[j]);
-      }
+      if (live[j]) probe_first<NARROW>(t, k[j], pr[j]);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (live[j])
-        upsert_or_spill<NARROW>(t, arena, ctr, k[j], (int64_t)c[j], slot[j], word[j], budget, n_new);
+      if (live[j]) upsert_or_spill<NARROW>(t, arena, ctr, k[j], (int64_t)c[j], pr[j], n_new);
   }
   if (n_new) atomicAdd(&s_new, n_new);
   __syncthreads();
@@ -516,7 +548,6 @@ insert_agg_kernel(const KeyT* __restrict__ keys,
                   Table t, Counters* ctr, double* special_vals, Arena arena,
                   int64_t thread_budget) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t budget = 0;   // drawn from ctr->budget in chunks
   (void)thread_budget;
   unsigned n_new = 0;
   const double nan = __longlong_as_double(0x7FF8000000000000ll);
@@ -532,7 +563,7 @@ insert_agg_kernel(const KeyT* __restrict__ keys,
       atomicAdd(&ctr->size[1], 1ull);
       vdst = special_vals + (int64_t)t.n_agg * 4;
     } else {
-      const int64_t slot = upsert_one<false>(t, ctr, k, 1, budget, n_new);
+      const int64_t slot = upsert_one<false>(t, k, 1, n_new);
       if (slot >= 0) {
         vdst = t.vals + slot * t.n_agg * 4;
       } else {
@@ -565,7 +596,6 @@ merge_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes
              const double* __restrict__ vals, int64_t n, Table t, Counters* ctr,
              double* special_vals, Arena arena, int64_t thread_budget) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t budget = 0;   // drawn from ctr->budget in chunks
   (void)thread_budget;
   unsigned n_new = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -576,7 +606,7 @@ merge_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes
       atomicAdd(&ctr->size[1], (unsigned long long)sizes[i]);
       vdst = special_vals + (int64_t)t.n_agg * 4;
     } else {
-      const int64_t slot = upsert_one<NARROW>(t, ctr, k, sizes[i], budget, n_new);
+      const int64_t slot = upsert_one<NARROW>(t, k, sizes[i], n_new);
       if (slot < 0) {
         const int64_t o = arena_claim(ctr);
         if (o < arena.cap) {
@@ -623,7 +653,14 @@ rehash_kernel(Table old_t, Table new_t) {
     int64_t slot = (int64_t)(table_mix64((uint64_t)k) & (uint64_t)mask);
     if (new_t.narrow) {
       const unsigned long long want = ((unsigned long long)sz << 32) | (unsigned long long)(unsigned)k;
-      while (atomicCAS(nb + slot, 0ull, want) != 0ull) slot = (slot + 1) & mask;
+      const int64_t bmask = (new_t.capacity >> 2) - 1;
+      int64_t b = (int64_t)(table_mix64((uint64_t)k) & (uint64_t)bmask);
+      bool placed = false;
+      while (!placed) {
+        for (int j = 0; j < 4 && !placed; ++j)
+          placed = (atomicCAS(nb + 4 * b + j, 0ull, want) == 0ull);
+        b = (b + 1) & bmask;
+      }
     } else {
       while ((long long)atomicCAS(nb + 2 * slot, (unsigned long long)kEmptyKey, (unsigned long long)k) != kEmptyKey)
         slot = (slot + 1) & mask;
@@ -1025,6 +1062,7 @@ extern "C" {
 
 int nvtb_hashagg_create(nvtb_hashagg_t** out, int n_agg, int64_t capacity_hint) {
   NVTB_REQUIRE(out != nullptr, "out is NULL");
+  ensure_pool_configured();
   NVTB_REQUIRE(n_agg >= 0 && n_agg <= kMaxAgg, "n_agg must be in [0, 8]");
   nvtb_hashagg* h = new (std::nothrow) nvtb_hashagg();
   NVTB_REQUIRE(h != nullptr, "host allocation failed");

@@ -33,6 +33,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int sm_count() {
+  ensure_pool_configured();
   static thread_local int cached_dev = -1;
   static thread_local int cached = 148;
   int dev = 0;
@@ -45,6 +46,18 @@ int sm_count() {
     cached_dev = dev;
   }
   return cached;
+}
+
+void ensure_pool_configured() {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_dev) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;   // never trim: the engine re-uses these buffers every batch
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done_dev = dev;
 }
 
 constexpr int kMaxCols = 32;  // columns per launch (kernel-parameter budget)

@@ -108,48 +108,58 @@ __global__ void lookup_build_kernel(const int64_t* __restrict__ keys, int64_t n,
   }
 }
 
-__device__ __forceinline__ int64_t lookup_first_slot(const Lookup& t, int64_t key) {
-  return (int64_t)(table_mix64((uint64_t)key) & (uint64_t)(t.capacity - 1));
-}
-
-struct SlotKV { long long k, v; };
+// A probe = the table words fetched for one key.
+//   narrow: one 32-byte sector = a 4-way bucket of packed (position+1, key) words,
+//           fetched with ONE 256-bit read-only load (L1-cacheable: the table is immutable).
+//   wide:   one {key, position} slot (128-bit load), linear probing.
+template <bool NARROW> struct LProbe;
+template <> struct LProbe<true>  { int64_t b; unsigned long long w[4]; };
+template <> struct LProbe<false> { int64_t b; long long k, v; };
 
 template <bool NARROW>
-__device__ __forceinline__ SlotKV lookup_load(const Lookup& t, int64_t slot) {
-  SlotKV r;
-  if (NARROW) {
-    const unsigned long long w = __ldg(reinterpret_cast<const unsigned long long*>(t.slots) + slot);
-    r.k = (long long)w;      // packed word (0 = empty)
-    r.v = 0;
+__device__ __forceinline__ void lookup_load(const Lookup& t, int64_t b, LProbe<NARROW>& p) {
+  p.b = b;
+  if constexpr (NARROW) {
+    const unsigned long long* a = reinterpret_cast<const unsigned long long*>(t.slots) + 4 * b;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(p.w[0]), "=l"(p.w[1]), "=l"(p.w[2]), "=l"(p.w[3]) : "l"(a));
   } else {
-    const longlong2 kv = __ldg(reinterpret_cast<const longlong2*>(t.slots + 2 * slot));
-    r.k = kv.x; r.v = kv.y;
+    const longlong2 kv = __ldg(reinterpret_cast<const longlong2*>(t.slots + 2 * b));
+    p.k = kv.x; p.v = kv.y;
   }
-  return r;
 }
 
-// position of `key` or -1, starting from a prefetched first probe.  Single exit:
-// the lanes of a warp iterate together (load factor <= 0.5 => ~1.5 probes).
 template <bool NARROW>
-__device__ __forceinline__ int64_t lookup_resolve(const Lookup& t, int64_t key, int64_t slot, SlotKV kv) {
+__device__ __forceinline__ int64_t lookup_home(const Lookup& t, int64_t key) {
+  const uint64_t h = table_mix64((uint64_t)key);
+  return NARROW ? (int64_t)(h & (uint64_t)((t.capacity >> 2) - 1)) : (int64_t)(h & (uint64_t)(t.capacity - 1));
+}
+
+// position of `key` or -1, starting from a prefetched first probe.  Single exit: the
+// lanes of a warp iterate together; with 4-way buckets almost every key resolves in
+// the first iteration.
+template <bool NARROW>
+__device__ __forceinline__ int64_t lookup_resolve(const Lookup& t, int64_t key, LProbe<NARROW> p) {
   if (!NARROW && key == kEmptyKey) return t.min_key_pos;
-  const int64_t mask = t.capacity - 1;
+  const int64_t mask = NARROW ? (t.capacity >> 2) - 1 : t.capacity - 1;
   int64_t pos = -1;
   bool done = false;
 #pragma unroll 1
   while (!done) {
-    if (NARROW) {
-      const unsigned long long w = (unsigned long long)kv.k;
-      if (w == 0ull) done = true;
-      else if ((unsigned)w == (unsigned)key) { pos = (int64_t)(w >> 32) - 1; done = true; }
+    if constexpr (NARROW) {
+      bool has_empty = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned long long w = p.w[j];
+        has_empty = has_empty || (w == 0ull);
+        if (w != 0ull && (unsigned)w == (unsigned)key) pos = (int64_t)(w >> 32) - 1;
+      }
+      done = (pos >= 0) || has_empty;       // a bucket with a free slot ends the probe sequence
     } else {
-      if (kv.k == key) { pos = kv.v; done = true; }
-      else if (kv.k == kEmptyKey) done = true;
+      if (p.k == key) { pos = p.v; done = true; }
+      else if (p.k == kEmptyKey) done = true;
     }
-    if (!done) {
-      slot = (slot + 1) & mask;
-      kv = lookup_load<NARROW>(t, slot);
-    }
+    if (!done) lookup_load<NARROW>(t, (p.b + 1) & mask, p);
   }
   return pos;
 }
@@ -157,11 +167,13 @@ __device__ __forceinline__ int64_t lookup_resolve(const Lookup& t, int64_t key, 
 __device__ __forceinline__ int64_t lookup_find(const Lookup& t, int64_t key) {
   if (t.narrow) {
     if (key < (int64_t)INT32_MIN || key > (int64_t)INT32_MAX) return -1;
-    const int64_t s = lookup_first_slot(t, key);
-    return lookup_resolve<true>(t, key, s, lookup_load<true>(t, s));
+    LProbe<true> p;
+    lookup_load<true>(t, lookup_home<true>(t, key), p);
+    return lookup_resolve<true>(t, key, p);
   }
-  const int64_t s = lookup_first_slot(t, key);
-  return lookup_resolve<false>(t, key, s, lookup_load<false>(t, s));
+  LProbe<false> p;
+  lookup_load<false>(t, lookup_home<false>(t, key), p);
+  return lookup_resolve<false>(t, key, p);
 }
 
 // number of leading rows with size >= threshold in a size-descending array
@@ -244,22 +256,24 @@ encode_kernel(const KeyT* __restrict__ keys, const uint8_t* __restrict__ mask,
 #pragma unroll
       for (int g = 0; g < kGroups; ++g) {
         const int64_t i = base + (int64_t)g * (kThreads * kRows) + (int64_t)threadIdx.x * kRows;
-        // (1) first-probe loads of all 8 keys back to back, (2) resolve, (3) one 256-bit store
-        int64_t slot[kRows];
-        SlotKV kv[kRows];
-#pragma unroll
-        for (int k = 0; k < kRows; ++k) {
-          slot[k] = lookup_first_slot(t, (long long)v[g][k]);
-          kv[k] = lookup_load<NARROW>(t, slot[k]);
-        }
+        // per half of 4 rows: (1) first-probe sector loads back to back, (2) resolve;
+        // then one 256-bit store (two for 8-byte labels) of the 8 labels
         OutT o[kRows];
 #pragma unroll
-        for (int k = 0; k < kRows; ++k) {
-          const bool valid = (m[g] >> k) & 1u;
-          const long long key = (long long)v[g][k];
-          int64_t pos = -1;
-          if (valid && in_range(key)) pos = lookup_resolve<NARROW>(t, key, slot[k], kv[k]);
-          o[k] = label_of(i + k, v[g][k], valid, pos);
+        for (int half = 0; half < 2; ++half) {
+          LProbe<NARROW> pr[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            lookup_load<NARROW>(t, lookup_home<NARROW>(t, (long long)v[g][4 * half + k]), pr[k]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = 4 * half + k;
+            const bool valid = (m[g] >> r) & 1u;
+            const long long key = (long long)v[g][r];
+            int64_t pos = -1;
+            if (valid && in_range(key)) pos = lookup_resolve<NARROW>(t, key, pr[k]);
+            o[r] = label_of(i + r, v[g][r], valid, pos);
+          }
         }
         st_rows8<OutT>(out + i, o);
       }
@@ -359,21 +373,15 @@ lookup_build_any_kernel(const int64_t* __restrict__ keys, int64_t n, int64_t* sl
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const long long k = keys[i];
     if (narrow) {
-      const unsigned key = (unsigned)(int)k;
-      const unsigned long long want = ((unsigned long long)(unsigned)(i + 1) << 32) | key;
-      int64_t slot = (int64_t)(table_mix64((uint64_t)k) & (uint64_t)mask);
-      while (true) {
-        unsigned long long prev = atomicCAS(ns + slot, 0ull, want);
-        if (prev == 0ull) break;
-        if ((unsigned)prev == key) {
-          while ((prev >> 32) > (unsigned long long)(i + 1)) {   // keep the smallest position
-            const unsigned long long seen = atomicCAS(ns + slot, prev, want);
-            if (seen == prev) break;
-            prev = seen;
-          }
-          break;
-        }
-        slot = (slot + 1) & mask;
+      // keys are distinct here (they come out of the aggregation table): claim the first
+      // free slot of the home bucket, spilling to the following buckets
+      const unsigned long long want = ((unsigned long long)(unsigned)(i + 1) << 32) | (unsigned)(int)k;
+      const int64_t bmask = (capacity >> 2) - 1;
+      int64_t b = (int64_t)(table_mix64((uint64_t)k) & (uint64_t)bmask);
+      bool placed = false;
+      while (!placed) {
+        for (int j = 0; j < 4 && !placed; ++j) placed = (atomicCAS(ns + 4 * b + j, 0ull, want) == 0ull);
+        b = (b + 1) & bmask;
       }
     } else {
       if (k == kEmptyKey) { *min_key_pos = i; continue; }
@@ -401,6 +409,122 @@ __global__ void lookup_init_any_kernel(int64_t* slots, int64_t capacity, const i
       slots[2 * s] = kEmptyKey;
       slots[2 * s + 1] = INT64_MAX;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// small vocabularies (n <= 8192): ONE single-CTA kernel does everything —
+// bitonic sort in shared memory on (size desc, key asc), freq_threshold /
+// max_size cut, meta sums, int32 check, and the lookup-table build.  Most
+// Criteo columns are this small; the general path (two cub radix sorts and a
+// dozen tiny launches) is launch-latency bound for them.
+// ---------------------------------------------------------------------------
+constexpr int kSmallVocabMax = 8192;
+constexpr int kSmallThreads = 1024;
+
+__device__ __forceinline__ bool vocab_before(long long sa, long long ka, long long sb, long long kb) {
+  return (sa > sb) || (sa == sb && ka < kb);
+}
+
+__global__ void __launch_bounds__(kSmallThreads)
+small_vocab_kernel(const int64_t* __restrict__ keys_in, const int64_t* __restrict__ sizes_in,
+                   int n, int n2, long long freq_threshold, long long max_keep,
+                   int64_t* __restrict__ keys_out, int64_t* __restrict__ sizes_out,
+                   int64_t* slots, long long capacity, VocabScalars* sc) {
+  extern __shared__ __align__(16) unsigned char small_raw[];
+  long long* k = reinterpret_cast<long long*>(small_raw);
+  long long* s = k + n2;
+  __shared__ long long red[3][kSmallThreads / 32];
+  __shared__ int s_keep, s_bad;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n2; i += kSmallThreads) {
+    k[i] = i < n ? (long long)keys_in[i] : (long long)INT64_MAX;
+    s[i] = i < n ? (long long)sizes_in[i] : -1ll;           // padding sorts last
+  }
+  if (tid == 0) { s_keep = 0; s_bad = 0; }
+  __syncthreads();
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (n2 >> 1); i += kSmallThreads) {
+        const int pos = 2 * i - (i & (stride - 1));
+        const int par = pos + stride;
+        const bool up = ((pos & size) == 0);
+        const long long sa = s[pos], ka = k[pos], sb = s[par], kb = k[par];
+        if (vocab_before(sb, kb, sa, ka) == up) { s[pos] = sb; k[pos] = kb; s[par] = sa; k[par] = ka; }
+      }
+      __syncthreads();
+    }
+  }
+  // cut
+  int n_keep = n;
+  if (freq_threshold > 0) {
+    int c = 0;
+    for (int i = tid; i < n; i += kSmallThreads) c += (s[i] >= freq_threshold) ? 1 : 0;
+    if (c) atomicAdd(&s_keep, c);
+    __syncthreads();
+    n_keep = s_keep;
+  } else if (max_keep >= 0) {
+    n_keep = (int)(max_keep < (long long)n ? max_keep : (long long)n);
+  }
+  // sums + int32 check
+  long long kept = 0, all = 0;
+  bool bad = false;
+  for (int i = tid; i < n; i += kSmallThreads) {
+    all += s[i];
+    if (i < n_keep) {
+      kept += s[i];
+      bad = bad || (k[i] < (long long)INT32_MIN) || (k[i] > (long long)INT32_MAX);
+    }
+    keys_out[i] = k[i];
+    sizes_out[i] = s[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kept += __shfl_down_sync(0xffffffffu, kept, o);
+    all += __shfl_down_sync(0xffffffffu, all, o);
+  }
+  if ((tid & 31) == 0) { red[0][tid >> 5] = kept; red[1][tid >> 5] = all; }
+  if (bad) s_bad = 1;
+  __syncthreads();
+  const bool narrow = (s_bad == 0);
+  // lookup table: init, then build from the first n_keep sorted keys
+  unsigned long long* ns = reinterpret_cast<unsigned long long*>(slots);
+  for (long long i = tid; i < capacity; i += kSmallThreads) {
+    if (narrow) ns[i] = 0ull;
+    else { slots[2 * i] = kEmptyKey; slots[2 * i + 1] = INT64_MAX; }
+  }
+  __syncthreads();
+  const long long mask = capacity - 1;
+  long long min_pos = -1;
+  for (int i = tid; i < n_keep; i += kSmallThreads) {
+    const long long key = k[i];
+    long long slot = (long long)(table_mix64((uint64_t)key) & (uint64_t)mask);
+    if (narrow) {
+      const unsigned long long want = ((unsigned long long)(unsigned)(i + 1) << 32) | (unsigned)(int)key;
+      const long long bmask = (capacity >> 2) - 1;
+      long long b = (long long)(table_mix64((uint64_t)key) & (uint64_t)bmask);
+      bool placed = false;
+      while (!placed) {                                   // keys are distinct
+        for (int j = 0; j < 4 && !placed; ++j) placed = (atomicCAS(ns + 4 * b + j, 0ull, want) == 0ull);
+        b = (b + 1) & bmask;
+      }
+    } else if (key == kEmptyKey) {
+      min_pos = i;
+    } else {
+      while ((long long)atomicCAS(reinterpret_cast<unsigned long long*>(slots + 2 * slot),
+                                  (unsigned long long)kEmptyKey, (unsigned long long)key) != kEmptyKey)
+        slot = (slot + 1) & mask;
+      slots[2 * slot + 1] = i;
+    }
+  }
+  if (min_pos >= 0) sc->min_key_pos = min_pos;
+  if (tid == 0) {
+    long long a = 0, b = 0;
+    for (int w = 0; w < kSmallThreads / 32; ++w) { a += red[0][w]; b += red[1][w]; }
+    sc->n_keep = n_keep;
+    sc->sum_kept = a;
+    sc->sum_all = b;
+    sc->fit_i32 = narrow ? 1 : 0;
   }
 }
 
@@ -469,6 +593,7 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* siz
                      int64_t max_size, int64_t num_buckets, void* stream) {
   NVTB_REQUIRE(out != nullptr && n >= 0, "out NULL or n < 0");
   NVTB_REQUIRE(n == 0 || (keys && sizes), "NULL keys/sizes");
+  ensure_pool_configured();
   NVTB_REQUIRE(!(freq_threshold > 0 && max_size > 0),
                "cannot use freq_threshold together with max_size");
   const int64_t oov_count = num_buckets > 0 ? num_buckets : 1;
@@ -483,6 +608,36 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* siz
   v->info.null_size = null_size;
   int64_t n_keep = n;
   VocabScalars* d_sc = nullptr;
+  if (n > 0 && n <= kSmallVocabMax) {
+    int n2 = 2;
+    while (n2 < n) n2 <<= 1;
+    NVTB_CUDA_OK(cudaMallocAsync(&v->keys, sizeof(int64_t) * n, st));
+    NVTB_CUDA_OK(cudaMallocAsync(&v->sizes, sizeof(int64_t) * n, st));
+    NVTB_CUDA_OK(cudaMallocAsync(&d_sc, sizeof(VocabScalars), st));
+    const VocabScalars init = {n, 0, 0, 1, -1};
+    NVTB_CUDA_OK(cudaMemcpyAsync(d_sc, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    v->t.capacity = pow2_at_least(2 * n);
+    v->t.min_key_pos = -1;
+    v->t.narrow = 0;
+    NVTB_CUDA_OK(cudaMallocAsync(&v->t.slots, sizeof(int64_t) * 2 * v->t.capacity, st));
+    const long long max_keep = max_size > 0 ? (long long)(max_size - (oov_count + 2)) : -1ll;
+    const int smem = n2 * 16;
+    NVTB_CUDA_OK(cudaFuncSetAttribute(small_vocab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallVocabMax * 16));
+    small_vocab_kernel<<<1, kSmallThreads, smem, st>>>(keys, sizes, (int)n, n2, (long long)freq_threshold, max_keep,
+                                                        v->keys, v->sizes, v->t.slots, (long long)v->t.capacity, d_sc);
+    NVTB_LAUNCH_OK();
+    VocabScalars h;
+    NVTB_CUDA_OK(cudaMemcpyAsync(&h, d_sc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    NVTB_CUDA_OK(cudaStreamSynchronize(st));
+    NVTB_CUDA_OK(cudaFreeAsync(d_sc, st));
+    v->info.n_kept = h.n_keep;
+    v->info.unique_size = h.sum_kept;
+    v->info.oov_size = h.sum_all - h.sum_kept;
+    v->t.narrow = h.fit_i32 ? 1 : 0;
+    v->t.min_key_pos = h.min_key_pos;
+    *out = v;
+    return NVTB_OK;
+  }
   if (n > 0) {
     // (1) key asc, (2) stable size desc  =>  (size desc, key asc)
     int64_t *k1 = nullptr, *s1 = nullptr, *k2 = nullptr, *s2 = nullptr;
