@@ -81,21 +81,36 @@ constexpr int kRows = 8;                            // rows per lane per group
 constexpr int kGroups = 2;                          // groups per thread per tile
 constexpr int kTile = kThreads * kRows * kGroups;   // 4096 rows
 
-// streaming loads: read-only path, no L1 allocation (each byte is used once)
+// L2 eviction policies.  Column data is streamed once: mark it evict-first so that
+// hundreds of MB of input/output do not wash the (much smaller) hash / lookup tables
+// out of the 126 MB L2; table sectors are marked evict-last.  (Non-volatile asm: the
+// compiler hoists the createpolicy out of the tile loops.)
+__device__ __forceinline__ uint64_t l2_evict_first() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_evict_last() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+// streaming loads: read-only path, no L1 allocation, L2 evict-first (each byte is used once)
 __device__ __forceinline__ void ld256(const void* __restrict__ p,
                                       uint32_t (&w)[8]) {
   asm volatile(
-      "ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      "ld.global.nc.L1::no_allocate.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
       : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]),
         "=r"(w[6]), "=r"(w[7])
-      : "l"(p));
+      : "l"(p), "l"(l2_evict_first()));
 }
 __device__ __forceinline__ void st256(void* p, const uint32_t (&w)[8]) {
   asm volatile(
-      "st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(
+      "st.global.L1::no_allocate.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(
           p),
       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]),
-      "r"(w[6]), "r"(w[7])
+      "r"(w[6]), "r"(w[7]), "l"(l2_evict_first())
       : "memory");
 }
 

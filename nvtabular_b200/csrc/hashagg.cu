@@ -111,6 +111,7 @@ struct nvtb_hashagg {
   double k_est;              // cardinality estimate (0 = none yet)
   int64_t hint;
   int n_agg;
+  bool mailbox_valid;        // mailbox == device counters (no launch / host edit since the readback)
 };
 
 namespace nvtb {
@@ -144,8 +145,8 @@ __device__ __forceinline__ void probe_load(const Table& t, int64_t b, Probe<NARR
   p.b = b;
   if constexpr (NARROW) {
     const unsigned long long* a = reinterpret_cast<const unsigned long long*>(t.slots) + 4 * b;
-    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(p.w[0]), "=l"(p.w[1]), "=l"(p.w[2]), "=l"(p.w[3]) : "l"(a));
+    asm volatile("ld.global.cg.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=l"(p.w[0]), "=l"(p.w[1]), "=l"(p.w[2]), "=l"(p.w[3]) : "l"(a), "l"(l2_evict_last()));
   } else {
     p.w[0] = __ldcg(reinterpret_cast<const unsigned long long*>(t.slots) + 2 * b);
   }
@@ -969,6 +970,7 @@ static int settle(nvtb_hashagg* h) {
     cudaStream_t st = h->pending_stream;
     NVTB_CUDA_OK(cudaEventSynchronize(h->ev));
     h->pending = false;
+    h->mailbox_valid = true;
     const Counters c = *h->mailbox;
     h->u_known = (int64_t)c.n_unique;
     const int64_t ovf = (int64_t)std::min<unsigned long long>(c.ovf_count, (unsigned long long)h->arena.cap);
@@ -1002,6 +1004,7 @@ static int post(nvtb_hashagg* h, cudaStream_t st) {
   NVTB_CUDA_OK(cudaMemcpyAsync(h->mailbox, h->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   NVTB_CUDA_OK(cudaEventRecord(h->ev, st));
   h->pending = true;
+  h->mailbox_valid = false;
   h->pending_stream = st;
   return NVTB_OK;
 }
@@ -1097,6 +1100,7 @@ int nvtb_hashagg_reset(nvtb_hashagg_t* h, void* stream) {
   NVTB_LAUNCH_OK();
   h->u_known = 0;
   h->rows_total = 0;
+  h->mailbox_valid = false;
   return NVTB_OK;
 }
 
@@ -1206,6 +1210,7 @@ int nvtb_hashagg_add_null_group(nvtb_hashagg_t* h, int64_t size, const double* v
   NVTB_CUDA_OK(cudaMemcpy(&s, h->ctr, sizeof(s), cudaMemcpyDeviceToHost));
   s.size[0] += (unsigned long long)size;
   NVTB_CUDA_OK(cudaMemcpy(h->ctr, &s, sizeof(s), cudaMemcpyHostToDevice));
+  h->mailbox_valid = false;
   if (h->n_agg > 0 && vals_host != nullptr) {
     double cur[4 * kMaxAgg];
     NVTB_CUDA_OK(cudaMemcpy(cur, h->special_vals, sizeof(double) * 4 * h->n_agg, cudaMemcpyDeviceToHost));
@@ -1231,8 +1236,11 @@ int nvtb_hashagg_size(nvtb_hashagg_t* h, int64_t* n_unique, int64_t* null_size, 
   cudaStream_t st = (cudaStream_t)stream;
   int rc = settle(h);
   if (rc) return rc;
-  NVTB_CUDA_OK(cudaMemcpyAsync(h->mailbox, h->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-  NVTB_CUDA_OK(cudaStreamSynchronize(st));
+  if (!h->mailbox_valid) {   // e.g. right after create/reset/add_null_group: read the counters
+    NVTB_CUDA_OK(cudaMemcpyAsync(h->mailbox, h->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    NVTB_CUDA_OK(cudaStreamSynchronize(st));
+    h->mailbox_valid = true;
+  }
   const Counters s = *h->mailbox;
   h->u_known = (int64_t)s.n_unique;
   if (n_unique) *n_unique = (int64_t)s.n_unique + (s.size[1] ? 1 : 0);

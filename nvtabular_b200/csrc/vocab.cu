@@ -16,7 +16,9 @@
 #include <algorithm>
 #include <cstddef>
 #include <cub/cub.cuh>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -121,8 +123,8 @@ __device__ __forceinline__ void lookup_load(const Lookup& t, int64_t b, LProbe<N
   p.b = b;
   if constexpr (NARROW) {
     const unsigned long long* a = reinterpret_cast<const unsigned long long*>(t.slots) + 4 * b;
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(p.w[0]), "=l"(p.w[1]), "=l"(p.w[2]), "=l"(p.w[3]) : "l"(a));
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=l"(p.w[0]), "=l"(p.w[1]), "=l"(p.w[2]), "=l"(p.w[3]) : "l"(a), "l"(l2_evict_last()));
   } else {
     const longlong2 kv = __ldg(reinterpret_cast<const longlong2*>(t.slots + 2 * b));
     p.k = kv.x; p.v = kv.y;
@@ -574,6 +576,14 @@ struct nvtb_vocab {
   int64_t* keys;   // device [n_kept], label order
   int64_t* sizes;  // device [n_kept] or nullptr
   nvtb_vocab_info_t info;
+  // nvtb_vocab_build enqueues everything and returns; the scalars it needs on the host
+  // (n_kept, meta sums, table layout) arrive in a pinned mailbox and are read by the first
+  // call that needs them (finalize) — so the 26 vocabularies of a Criteo fit are built
+  // back to back without a host round trip in between.
+  nvtb::VocabScalars* d_sc;
+  nvtb::VocabScalars* h_sc;   // slot in the pinned pool
+  cudaEvent_t ev;
+  bool pending;
 };
 
 struct nvtb_groupstats {
@@ -583,6 +593,72 @@ struct nvtb_groupstats {
   int width;
   int64_t null_row;
 };
+
+namespace nvtb {
+
+// tiny pinned slab for the per-vocabulary mailboxes (cudaMallocHost per handle is slow)
+static std::mutex g_pin_mu;
+static VocabScalars* g_pin_slab = nullptr;
+static std::vector<int> g_pin_free;
+constexpr int kPinSlots = 8192;
+
+static VocabScalars* pin_acquire() {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  if (g_pin_slab == nullptr) {
+    if (cudaMallocHost(&g_pin_slab, sizeof(VocabScalars) * kPinSlots) != cudaSuccess) return nullptr;
+    for (int i = kPinSlots - 1; i >= 0; --i) g_pin_free.push_back(i);
+  }
+  if (g_pin_free.empty()) return nullptr;
+  const int i = g_pin_free.back();
+  g_pin_free.pop_back();
+  return g_pin_slab + i;
+}
+static void pin_release(VocabScalars* p) {
+  if (p == nullptr) return;
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  g_pin_free.push_back((int)(p - g_pin_slab));
+}
+
+static int vocab_finalize(nvtb_vocab* v) {
+  if (!v->pending) return NVTB_OK;
+  NVTB_CUDA_OK(cudaEventSynchronize(v->ev));
+  const VocabScalars h = *v->h_sc;
+  v->info.n_kept = h.n_keep;
+  v->info.unique_size = h.sum_kept;
+  v->info.oov_size = h.sum_all - h.sum_kept;
+  v->t.narrow = h.fit_i32 ? 1 : 0;   // exactly what the device-side init/build kernels used
+  v->t.min_key_pos = h.min_key_pos;
+  v->pending = false;
+  if (v->d_sc) { cudaFreeAsync(v->d_sc, 0); v->d_sc = nullptr; }
+  pin_release(v->h_sc);
+  v->h_sc = nullptr;
+  return NVTB_OK;
+}
+
+// enqueue the readback of the device scalars; falls back to a blocking read when the
+// pinned pool is exhausted
+static int vocab_post(nvtb_vocab* v, cudaStream_t st) {
+  v->h_sc = pin_acquire();
+  if (v->h_sc == nullptr || cudaEventCreateWithFlags(&v->ev, cudaEventDisableTiming) != cudaSuccess) {
+    VocabScalars h;
+    NVTB_CUDA_OK(cudaMemcpyAsync(&h, v->d_sc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    NVTB_CUDA_OK(cudaStreamSynchronize(st));
+    static VocabScalars tmp;
+    VocabScalars* keep = v->h_sc;
+    v->h_sc = &tmp; tmp = h; v->pending = true; v->ev = nullptr;
+    // emulate finalize without an event
+    v->info.n_kept = h.n_keep; v->info.unique_size = h.sum_kept; v->info.oov_size = h.sum_all - h.sum_kept;
+    v->t.narrow = h.fit_i32 ? 1 : 0; v->t.min_key_pos = h.min_key_pos; v->pending = false;
+    cudaFreeAsync(v->d_sc, st); v->d_sc = nullptr; v->h_sc = nullptr; pin_release(keep);
+    return NVTB_OK;
+  }
+  NVTB_CUDA_OK(cudaMemcpyAsync(v->h_sc, v->d_sc, sizeof(VocabScalars), cudaMemcpyDeviceToHost, st));
+  NVTB_CUDA_OK(cudaEventRecord(v->ev, st));
+  v->pending = true;
+  return NVTB_OK;
+}
+
+}  // namespace nvtb
 
 using namespace nvtb;
 
@@ -626,15 +702,9 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* siz
     small_vocab_kernel<<<1, kSmallThreads, smem, st>>>(keys, sizes, (int)n, n2, (long long)freq_threshold, max_keep,
                                                         v->keys, v->sizes, v->t.slots, (long long)v->t.capacity, d_sc);
     NVTB_LAUNCH_OK();
-    VocabScalars h;
-    NVTB_CUDA_OK(cudaMemcpyAsync(&h, d_sc, sizeof(h), cudaMemcpyDeviceToHost, st));
-    NVTB_CUDA_OK(cudaStreamSynchronize(st));
-    NVTB_CUDA_OK(cudaFreeAsync(d_sc, st));
-    v->info.n_kept = h.n_keep;
-    v->info.unique_size = h.sum_kept;
-    v->info.oov_size = h.sum_all - h.sum_kept;
-    v->t.narrow = h.fit_i32 ? 1 : 0;
-    v->t.min_key_pos = h.min_key_pos;
+    v->d_sc = d_sc;
+    int rc = vocab_post(v, st);
+    if (rc) { nvtb_vocab_destroy(v); return rc; }
     *out = v;
     return NVTB_OK;
   }
@@ -686,14 +756,9 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* siz
   int rc = lookup_create(&v->t, v->keys, n_keep, d_sc ? &d_sc->fit_i32 : nullptr, st);
   if (rc) { nvtb_vocab_destroy(v); return rc; }
   if (d_sc) {
-    VocabScalars h;
-    NVTB_CUDA_OK(cudaMemcpyAsync(&h, d_sc, sizeof(h), cudaMemcpyDeviceToHost, st));
-    NVTB_CUDA_OK(cudaStreamSynchronize(st));
-    NVTB_CUDA_OK(cudaFreeAsync(d_sc, st));
-    v->info.unique_size = h.sum_kept;
-    v->info.oov_size = h.sum_all - h.sum_kept;
-    v->t.narrow = h.fit_i32 ? 1 : 0;   // exactly what the device-side init/build kernels used
-    v->t.min_key_pos = h.min_key_pos;
+    v->d_sc = d_sc;
+    rc = vocab_post(v, st);
+    if (rc) { nvtb_vocab_destroy(v); return rc; }
   } else {
     NVTB_CUDA_OK(cudaStreamSynchronize(st));
   }
@@ -727,6 +792,8 @@ int nvtb_vocab_from_arrays(nvtb_vocab_t** out, const int64_t* keys, const int64_
 
 int nvtb_vocab_destroy(nvtb_vocab_t* v) {
   if (v == nullptr) return NVTB_OK;
+  vocab_finalize(v);
+  if (v->ev) cudaEventDestroy(v->ev);
   // stream-ordered frees on the legacy default stream: ordered after every kernel
   // that may still probe the table, without a device-wide host sync
   if (v->t.slots) cudaFreeAsync(v->t.slots, 0);
@@ -738,12 +805,14 @@ int nvtb_vocab_destroy(nvtb_vocab_t* v) {
 
 int nvtb_vocab_info(const nvtb_vocab_t* v, nvtb_vocab_info_t* info) {
   NVTB_REQUIRE(v != nullptr && info != nullptr, "NULL argument");
+  { int frc = vocab_finalize(const_cast<nvtb_vocab_t*>(v)); if (frc) return frc; }
   *info = v->info;
   return NVTB_OK;
 }
 
 int nvtb_vocab_export(const nvtb_vocab_t* v, int64_t* keys_out, int64_t* sizes_out, void* stream) {
   NVTB_REQUIRE(v != nullptr, "NULL vocab");
+  { int frc = vocab_finalize(const_cast<nvtb_vocab_t*>(v)); if (frc) return frc; }
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = v->info.n_kept;
   if (n == 0) return NVTB_OK;
@@ -761,6 +830,7 @@ int nvtb_encode_apply(const nvtb_vocab_t* v, const nvtb_col_t* key, int64_t n,
                       uint64_t num_buckets, const nvtb_col_t* hash_cols, int n_hash_cols,
                       void* out, int out_dtype, void* stream) {
   NVTB_REQUIRE(v != nullptr && key != nullptr && n >= 0, "NULL argument or n < 0");
+  { int frc = vocab_finalize(const_cast<nvtb_vocab_t*>(v)); if (frc) return frc; }
   NVTB_REQUIRE(key->dtype == NVTB_I32 || key->dtype == NVTB_I64, "key dtype must be int32 or int64");
   NVTB_REQUIRE(out_dtype == NVTB_I32 || out_dtype == NVTB_I64, "out_dtype must be int32 or int64");
   NVTB_REQUIRE(n_hash_cols >= 0 && n_hash_cols <= kMaxHashCols, "n_hash_cols must be in [0, 8]");

@@ -110,7 +110,8 @@ class Moments:
         """Cross-GPU merge: one NCCL all-reduce of 3 sums + min + max per column
         (replaces the dask tree of moments.py:45-55)."""
         import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        from .dist import world
+        if world()[0] <= 1:
             return
         a = self.acc.view(self.ncols, 5)
         sums = a[:, 0:3].contiguous()
@@ -328,13 +329,29 @@ class Vocab:
     """Ordered vocabulary + device lookup (nvtb_vocab_*; replaces
     _write_uniques/_save_encodings/_encode, categorify.py:1149-1337,719-822,1558-1807)."""
 
-    def __init__(self, handle, lib):
+    def __init__(self, handle, lib, n_total=None):
         self.h = handle
         self.lib = lib
-        info = _lib.nvtb_vocab_info_t()
-        _lib.check(lib.nvtb_vocab_info(self.h, byref(info)))
-        self.n_kept, self.n_total = info.n_kept, info.n_total
-        self.null_size, self.oov_size, self.unique_size = info.null_size, info.oov_size, info.unique_size
+        self._info = None
+        self._n_total = n_total
+
+    def _load(self):
+        """nvtb_vocab_build only ENQUEUES the build; the scalars come back through a pinned
+        mailbox and are read (one event wait) the first time anything asks for them."""
+        if self._info is None:
+            info = _lib.nvtb_vocab_info_t()
+            _lib.check(self.lib.nvtb_vocab_info(self.h, byref(info)))
+            self._info = info
+        return self._info
+
+    n_kept = property(lambda self: self._load().n_kept)
+    null_size = property(lambda self: self._load().null_size)
+    oov_size = property(lambda self: self._load().oov_size)
+    unique_size = property(lambda self: self._load().unique_size)
+
+    @property
+    def n_total(self):
+        return self._n_total if self._n_total is not None else self._load().n_total
 
     @classmethod
     def build(cls, keys: torch.Tensor, sizes: torch.Tensor, null_size=0, freq_threshold=0,
@@ -347,7 +364,7 @@ class Vocab:
                                             int(freq_threshold or 0), int(max_size or 0), int(num_buckets or 0),
                                             _lib.stream_ptr()))
         _count(8)
-        return cls(h, lib)
+        return cls(h, lib, n_total=keys.numel())
 
     @classmethod
     def from_arrays(cls, keys: torch.Tensor, sizes: Optional[torch.Tensor] = None):
