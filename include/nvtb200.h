@@ -215,7 +215,6 @@ int nvtb_pack_keys2(const nvtb_col_t* a_host, const nvtb_col_t* b_host,
  * (keep the first max_size - (num_buckets or 1) - 2), and build the
  * key -> position lookup used by the encode.  keys/sizes are device arrays of
  * length n (unordered, distinct keys, null group NOT included).
- * Synchronises (sizes are returned to the host through nvtb_vocab_info).
  *
  * nvtb_vocab_from_arrays: keys already in label order (user `vocabs=`,
  * categorify.py:421-454, or a unique.<col>.parquet read back); sizes may be
@@ -229,10 +228,15 @@ typedef struct {
   int64_t oov_size;    /* meta num_observed[oov]: rows of dropped keys    */
   int64_t unique_size; /* meta num_observed[unique]                       */
 } nvtb_vocab_info_t;
+/* key_bits: 32 when every key is known to be an int32 value (halves the radix passes),
+ * else 0; size_bound: an upper bound on any size (e.g. rows seen), 0 = unknown.
+ * Both are speed hints only.  The build is ENQUEUED: n_kept and the meta numbers are read
+ * back by the first nvtb_vocab_info / export / encode call on the handle. */
 int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys,
                      const int64_t* sizes, int64_t n, int64_t null_size,
                      int64_t freq_threshold, int64_t max_size,
-                     int64_t num_buckets, void* stream);
+                     int64_t num_buckets, int key_bits, int64_t size_bound,
+                     void* stream);
 int nvtb_vocab_from_arrays(nvtb_vocab_t** out, const int64_t* keys,
                            const int64_t* sizes, int64_t n, void* stream);
 int nvtb_vocab_destroy(nvtb_vocab_t* v);

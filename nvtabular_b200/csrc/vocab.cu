@@ -336,6 +336,12 @@ struct VocabScalars {
   long long min_key_pos;   // position of the INT64_MIN key, or -1
 };
 
+__global__ void __launch_bounds__(kThreads)
+xor_copy_kernel(const int64_t* src, int64_t* dst, int64_t n, long long mask) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i] ^ mask;
+}
+
 // sums of the kept / all sizes, and "do the kept keys fit int32?"
 __global__ void __launch_bounds__(kThreads)
 vocab_scalars_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes,
@@ -666,7 +672,8 @@ extern "C" {
 
 int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* sizes,
                      int64_t n, int64_t null_size, int64_t freq_threshold,
-                     int64_t max_size, int64_t num_buckets, void* stream) {
+                     int64_t max_size, int64_t num_buckets, int key_bits,
+                     int64_t size_bound, void* stream) {
   NVTB_REQUIRE(out != nullptr && n >= 0, "out NULL or n < 0");
   NVTB_REQUIRE(n == 0 || (keys && sizes), "NULL keys/sizes");
   ensure_pool_configured();
@@ -715,14 +722,35 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* siz
     NVTB_CUDA_OK(cudaMallocAsync(&s1, sizeof(int64_t) * n, st));
     NVTB_CUDA_OK(cudaMallocAsync(&k2, sizeof(int64_t) * n, st));
     NVTB_CUDA_OK(cudaMallocAsync(&s2, sizeof(int64_t) * n, st));
+    // radix passes are the cost here: sort only the bits that can differ.  Keys known to
+    // be int32 values (sign-extended) are biased by 2^31 (flip bit 31) so that their low 32
+    // bits order them; sizes are bounded by the number of rows seen.
+    const bool key32 = (key_bits > 0 && key_bits <= 32);
+    int size_bits = 64;
+    if (size_bound > 0) {
+      size_bits = 1;
+      while (size_bits < 63 && ((int64_t)1 << size_bits) <= size_bound) ++size_bits;
+    }
+    const int g_x = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
+    const int64_t* sort_in = keys;
+    if (key32) {
+      xor_copy_kernel<<<g_x, kThreads, 0, st>>>(keys, k2, n, 0x80000000ll);   // k2 is free until the 2nd sort
+      NVTB_LAUNCH_OK();
+      sort_in = k2;
+    }
+    const int kb = key32 ? 32 : 64;
     size_t tmp_a = 0, tmp_b = 0;
-    NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_a, keys, k1, sizes, s1, n, 0, 64, st));
-    NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_b, s1, s2, k1, k2, n, 0, 64, st));
+    NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_a, sort_in, k1, sizes, s1, n, 0, kb, st));
+    NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_b, s1, s2, k1, k2, n, 0, size_bits, st));
     size_t tmp_bytes = std::max(tmp_a, tmp_b);
     void* tmp = nullptr;
     NVTB_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, st));
-    NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, k1, sizes, s1, n, 0, 64, st));
-    NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, s1, s2, k1, k2, n, 0, 64, st));
+    NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, sort_in, k1, sizes, s1, n, 0, kb, st));
+    if (key32) {
+      xor_copy_kernel<<<g_x, kThreads, 0, st>>>(k1, k1, n, 0x80000000ll);     // undo the bias
+      NVTB_LAUNCH_OK();
+    }
+    NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, s1, s2, k1, k2, n, 0, size_bits, st));
     NVTB_CUDA_OK(cudaFreeAsync(k1, st));
     NVTB_CUDA_OK(cudaFreeAsync(s1, st));
     NVTB_CUDA_OK(cudaFreeAsync(tmp, st));

@@ -355,14 +355,14 @@ class Vocab:
 
     @classmethod
     def build(cls, keys: torch.Tensor, sizes: torch.Tensor, null_size=0, freq_threshold=0,
-              max_size=0, num_buckets=0):
+              max_size=0, num_buckets=0, key_bits=0, size_bound=0):
         _lib.require_cuda()
         lib = _lib.load()
         h = c_void_p()
         with _timed("vocab_build", float(keys.numel() * 16)):
             _lib.check(lib.nvtb_vocab_build(byref(h), _ptr(keys), _ptr(sizes), keys.numel(), int(null_size),
                                             int(freq_threshold or 0), int(max_size or 0), int(num_buckets or 0),
-                                            _lib.stream_ptr()))
+                                            int(key_bits), int(size_bound), _lib.stream_ptr()))
         _count(8)
         return cls(h, lib, n_total=keys.numel())
 

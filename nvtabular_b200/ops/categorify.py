@@ -199,6 +199,7 @@ class Categorify(StatOperator):
                           "consistent on GPU and CPU with this num_buckets setting!")
         self._user_vocabs = vocabs
         self._aggs = {}      # storage name -> engine.HashAgg, reused (reset) across fits
+        self._rows_seen = {}
         self.vocabs = {}
         self.categories = _Categories()
         if vocabs is not None:
@@ -294,9 +295,12 @@ class Categorify(StatOperator):
                 for storage, names in groups:
                     space, agg = state[storage]
                     for n in names:
-                        agg.insert(space.keys_for(part[n]))
+                        self._insert(storage, agg, space.keys_for(part[n]))
                 part = next(it, None)
-            return {storage: self._close_group(storage, [storage], *state[storage]) for storage, names in groups}
+            from ..dist import global_merge_many
+            merged = global_merge_many([state[storage][1] for storage, _ in groups])
+            return {storage: self._close_group(storage, [storage], state[storage][0], state[storage][1], m)
+                    for (storage, names), m in zip(groups, merged)}
         parts = [first] + list(it)   # strings / general combos need a dictionary pre-pass
         fitted = {}
         for storage, names in groups:
@@ -317,19 +321,32 @@ class Categorify(StatOperator):
             agg = self._aggs[storage] = engine.HashAgg(0)
         else:
             agg.reset()
+        self._rows_seen[storage] = 0
         return agg
+
+    def _insert(self, storage, agg, key):
+        agg.insert(key)
+        self._rows_seen[storage] += key.data.numel()
+
+    def _size_bound(self, storage) -> int:
+        """upper bound on any group's size (speed hint for the radix sort); unknown across GPUs"""
+        from ..dist import world
+        return self._rows_seen.get(storage, 0) if world()[0] == 1 else 0
 
     def _open_group(self, storage, names, df):
         space = KeySpace.for_columns([_leaf(df[n]) for n in names])
         return space, self._get_agg(storage)
 
-    def _close_group(self, storage, key_names, space, agg) -> FittedVocab:
-        keys, sizes, null_size = _global_unique_merge(agg)
+    def _close_group(self, storage, key_names, space, agg, merged=None) -> FittedVocab:
+        keys, sizes, null_size = merged if merged is not None else _global_unique_merge(agg)
         ft = _resolve(self.freq_threshold, storage, 0) or 0
         ms = _resolve(self.max_size, storage, 0) or 0
         nb = self._nb(storage)
         try:
-            vocab = engine.Vocab.build(keys, sizes, null_size, ft, ms, nb or 0)
+            key_bits = 32 if isinstance(space, KeySpace) and (space.kind == "str" or (
+                space.kind == "int" and space.np_dtype == np.dtype("int32"))) else 0
+            vocab = engine.Vocab.build(keys, sizes, null_size, ft, ms, nb or 0, key_bits,
+                                       self._size_bound(storage))
         except Exception as e:
             if "max_size" in str(e):     # categorify.py:1206-1211
                 raise ValueError(
@@ -361,10 +378,10 @@ class Categorify(StatOperator):
         agg = self._get_agg(storage)
         for df in parts:
             if combo:
-                agg.insert(space.keys_for([df[n] for n in names]))
+                self._insert(storage, agg, space.keys_for([df[n] for n in names]))
             else:
                 for n in names:          # joint encoding: every column feeds the SAME table
-                    agg.insert(space.keys_for(df[n]))
+                    self._insert(storage, agg, space.keys_for(df[n]))
         return self._close_group(storage, key_names, space, agg)
 
     def fit_finalize(self, categories):

@@ -89,6 +89,24 @@ def main():
     res = {"keys": k.numpy()[order].tolist(), "sizes": s.numpy()[order].tolist(),
            "vals": v.numpy()[order].reshape(len(order), -1).tolist(), "null_size": ns, "null_vals": nv.tolist(),
            "local_keys": keys.tolist(), "local_x": x.tolist()}
+    # many keys-only tables at once (the Categorify path)
+    from nvtabular_b200.dist import global_merge_many
+    many = []
+    local_cols = []
+    for c in range(5):
+        kk = rng.integers(0, 50 * (c + 1), 2000)
+        a = FakeAgg(0)
+        for key in kk.tolist():
+            a.merge(torch.tensor([key]), torch.tensor([1]))
+        a.null_size = c + rank
+        many.append(a)
+        local_cols.append(kk.tolist())
+    merged = global_merge_many(many, engine=FakeEngine)
+    res["many"] = []
+    for (mk, ms, mns) in merged:
+        o = np.argsort(mk.numpy())
+        res["many"].append({"keys": mk.numpy()[o].tolist(), "sizes": ms.numpy()[o].tolist(), "null": mns})
+    res["many_local"] = local_cols
     t = allgather_var(torch.arange(rank + 2, dtype=torch.int64))
     res["allgather_var"] = t.tolist()
     with open(os.path.join(out_dir, f"rank{rank}.json"), "w") as f:

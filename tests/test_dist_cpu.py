@@ -37,3 +37,10 @@ def test_owner_exchange_two_ranks_gloo(tmp_path):
     assert res[0]["null_size"] == 7 + 8
     np.testing.assert_allclose(res[0]["null_vals"], [[3.0, 4.0, -4.0, 5.0]])
     assert res[0]["allgather_var"] == [0, 1, 0, 1, 2]
+    # batched multi-table merge: identical on both ranks and equal to the union's value_counts
+    assert res[0]["many"] == res[1]["many"]
+    for c in range(5):
+        vc = pd.Series(res[0]["many_local"][c] + res[1]["many_local"][c]).value_counts().sort_index()
+        assert res[0]["many"][c]["keys"] == vc.index.tolist()
+        assert res[0]["many"][c]["sizes"] == vc.tolist()
+        assert res[0]["many"][c]["null"] == 2 * c + 1

@@ -318,7 +318,7 @@ def test_vocab_build_and_encode(eng, freq_threshold, max_size, num_buckets):
     h = eng.HashAgg(0)
     h.insert(col)
     keys, sizes, _, null_size, _ = h.export()
-    v = eng.Vocab.build(keys, sizes, null_size, freq_threshold, max_size, num_buckets)
+    v = eng.Vocab.build(keys, sizes, null_size, freq_threshold, max_size, num_buckets, key_bits=32, size_bound=n)
     df = pd.DataFrame({"c": _series(arr, mask)})
     o = CategorifyOracle(["c"], freq_threshold=freq_threshold, max_size=max_size,
                          num_buckets=num_buckets or None).fit(df)
