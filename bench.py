@@ -37,6 +37,21 @@ def _peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _traffic(kernel, rows):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed ncu capture (profiles/traffic_r1.json; produced by tools/summarize_ncu.py).
+    Only valid for the row count it was captured at; null otherwise."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
+            d = json.load(f)
+        e = d.get(kernel)
+        if e and int(e.get("rows_per_gpu", -1)) == int(rows):
+            return float(e["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -268,7 +283,7 @@ def main():
         d = fam[dominant]
         ach = d["bytes"] / (d["ms"] / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": ach / peak, "traffic": _traffic(dominant, rows), "peak_source": peak_src,
                     "avg_launch_ms": d["ms"] / d["launches"],
                     "algorithmic_bytes_per_launch": d["bytes"] / d["launches"],
                     "share_of_step": (d["ms"] / args.steps) / ms_per_step,

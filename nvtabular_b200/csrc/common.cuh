@@ -348,6 +348,17 @@ __host__ __device__ __forceinline__ uint64_t table_mix64(uint64_t k) {
   return k;
 }
 
+// 32-bit variant (murmur3 fmix32) for the narrow (int32-key) tables: a third of the
+// instructions of the 64-bit mixer, which matters in the per-row paths.
+__host__ __device__ __forceinline__ uint32_t table_mix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+
 constexpr int64_t kEmptyKey = INT64_MIN;  // table sentinel (see hashagg.cu)
 
 // dtype dispatch for column-typed kernels

@@ -154,8 +154,9 @@ __device__ __forceinline__ void probe_load(const Table& t, int64_t b, Probe<NARR
 
 template <bool NARROW>
 __device__ __forceinline__ int64_t probe_home(const Table& t, int64_t key) {
-  const uint64_t h = table_mix64((uint64_t)key);
-  return NARROW ? (int64_t)(h & (uint64_t)((t.capacity >> 2) - 1)) : (int64_t)(h & (uint64_t)(t.capacity - 1));
+  if constexpr (NARROW)   // int32 keys: 32-bit mixer, low bits pick the bucket
+    return (int64_t)((uint64_t)table_mix32((uint32_t)(int32_t)key) & (uint64_t)((t.capacity >> 2) - 1));
+  return (int64_t)(table_mix64((uint64_t)key) & (uint64_t)(t.capacity - 1));
 }
 
 template <bool NARROW>
@@ -331,9 +332,9 @@ template <> struct SmemAgg<int32_t> {
     return done;
   }
   // fold one key; true = absorbed.  `hits` counts keys that were already present.
-  __device__ __forceinline__ bool fold(long long k, uint64_t h, unsigned& hits) {
+  __device__ __forceinline__ bool fold(long long k, unsigned& hits) {
     const unsigned key = (unsigned)(int)k;
-    const unsigned b = (unsigned)(h >> 40) & (kBuckets - 1);     // bits disjoint from the global slot bits
+    const unsigned b = (table_mix32(key) >> 20) & (kBuckets - 1);   // top bits; the global bucket uses the low bits
     unsigned long long x, y;
     const unsigned addr = (unsigned)__cvta_generic_to_shared(w + 2 * b);
     asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(addr));
@@ -380,8 +381,8 @@ template <> struct SmemAgg<int64_t> {
     }
     return done;
   }
-  __device__ __forceinline__ bool fold(long long k, uint64_t h, unsigned& hits) {
-    const unsigned s = (unsigned)(h >> 40) & (kSlots - 1);
+  __device__ __forceinline__ bool fold(long long k, unsigned& hits) {
+    const unsigned s = (unsigned)(table_mix64((uint64_t)k) >> 40) & (kSlots - 1);
     if (*reinterpret_cast<volatile long long*>(&keys[s]) == k) {
       atomicAdd(&cnt[s], 1u);
       hits++;
@@ -427,7 +428,7 @@ insert_keys_kernel(const KeyT* __restrict__ keys,
       n_min += is_min ? 1u : 0u;
       if (valid && !is_min) {
         rows++;
-        if (bypass || !sm.fold(key, table_mix64((uint64_t)key), hits)) pend |= 1u << k;
+        if (bypass || !sm.fold(key, hits)) pend |= 1u << k;
       }
     }
     // global phase in two halves of 4 keys: 4 sector loads in flight per thread
@@ -470,7 +471,7 @@ insert_keys_kernel(const KeyT* __restrict__ keys,
         const long long key = (long long)keys[i];
         if (sizeof(KeyT) == 8 && key == kEmptyKey) { n_min++; continue; }
         rows++;
-        if (!bypass && sm.fold(key, table_mix64((uint64_t)key), hits)) continue;
+        if (!bypass && sm.fold(key, hits)) continue;
         Probe<NARROW> pr;
         probe_first<NARROW>(t, key, pr);
         upsert_or_spill<NARROW>(t, arena, ctr, key, 1, pr, n_new);
@@ -599,33 +600,47 @@ merge_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   (void)thread_budget;
   unsigned n_new = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += stride) {
-    const long long k = keys[i];
-    double* vdst;
-    if (!NARROW && k == kEmptyKey) {
-      atomicAdd(&ctr->size[1], (unsigned long long)sizes[i]);
-      vdst = special_vals + (int64_t)t.n_agg * 4;
-    } else {
-      const int64_t slot = upsert_one<NARROW>(t, k, sizes[i], n_new);
-      if (slot < 0) {
-        const int64_t o = arena_claim(ctr);
-        if (o < arena.cap) {
-          arena.keys[o] = k;
-          arena.sizes[o] = sizes[i];
-          if (vals != nullptr)
-            for (int j = 0; j < t.n_agg * 4; ++j)
-              arena.vals[o * t.n_agg * 4 + j] = vals[i * t.n_agg * 4 + j];
-        }
-        continue;
-      }
-      vdst = NARROW ? nullptr : t.vals + slot * t.n_agg * 4;
+  // four rows per thread per step: their first probes are issued back to back
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+    long long k[4];
+    bool live[4];
+    Probe<NARROW> pr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = i0 + j * stride;
+      live[j] = i < n;
+      k[j] = live[j] ? keys[i] : 0;
+      if (live[j] && (NARROW || k[j] != kEmptyKey)) probe_first<NARROW>(t, k[j], pr[j]);
     }
-    if (vals != nullptr && vdst != nullptr)
-      for (int j = 0; j < t.n_agg; ++j) {
-        const double* v = vals + (i * t.n_agg + j) * 4;
-        vals_combine(vdst + j * 4, v[0], v[1], v[2], v[3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!live[j]) continue;
+      const int64_t i = i0 + j * stride;
+      double* vdst;
+      if (!NARROW && k[j] == kEmptyKey) {
+        atomicAdd(&ctr->size[1], (unsigned long long)sizes[i]);
+        vdst = special_vals + (int64_t)t.n_agg * 4;
+      } else {
+        const int64_t slot = upsert_add<NARROW>(t, k[j], sizes[i], pr[j], n_new);
+        if (slot < 0) {
+          const int64_t o = arena_claim(ctr);
+          if (o < arena.cap) {
+            arena.keys[o] = k[j];
+            arena.sizes[o] = sizes[i];
+            if (vals != nullptr)
+              for (int q = 0; q < t.n_agg * 4; ++q)
+                arena.vals[o * t.n_agg * 4 + q] = vals[i * t.n_agg * 4 + q];
+          }
+          continue;
+        }
+        vdst = NARROW ? nullptr : t.vals + slot * t.n_agg * 4;
       }
+      if (vals != nullptr && vdst != nullptr)
+        for (int q = 0; q < t.n_agg; ++q) {
+          const double* v = vals + (i * t.n_agg + q) * 4;
+          vals_combine(vdst + q * 4, v[0], v[1], v[2], v[3]);
+        }
+    }
   }
   if (n_new) atomicAdd(&ctr->n_unique, (unsigned long long)n_new);
 }
@@ -655,7 +670,7 @@ rehash_kernel(Table old_t, Table new_t) {
     if (new_t.narrow) {
       const unsigned long long want = ((unsigned long long)sz << 32) | (unsigned long long)(unsigned)k;
       const int64_t bmask = (new_t.capacity >> 2) - 1;
-      int64_t b = (int64_t)(table_mix64((uint64_t)k) & (uint64_t)bmask);
+      int64_t b = (int64_t)((uint64_t)table_mix32((uint32_t)(int32_t)k) & (uint64_t)bmask);
       bool placed = false;
       while (!placed) {
         for (int j = 0; j < 4 && !placed; ++j)
@@ -750,14 +765,41 @@ owner_count_kernel(const int64_t* __restrict__ keys, int64_t n, int n_parts,
     atomicAdd(&counts[threadIdx.x], (unsigned long long)sc[threadIdx.x]);
 }
 
+// scatter pass: each CTA ranks its chunk of rows per owner in shared memory and reserves
+// ONE contiguous range per owner with a single global atomic, instead of one global
+// atomic per row on only `n_parts` addresses (which serialised at ~1 row/ns).
 __global__ void __launch_bounds__(kThreads)
 owner_scatter_kernel(const int64_t* __restrict__ keys, int64_t n, int n_parts,
                      unsigned long long* cursors, int64_t* __restrict__ perm) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int o = owner_of(keys[i], n_parts);
-    const unsigned long long pos = atomicAdd(&cursors[o], 1ull);
-    perm[pos] = i;
+  constexpr int kPer = 8;                       // rows per thread per chunk
+  __shared__ unsigned int s_cnt[64];
+  __shared__ unsigned long long s_base[64];
+  const int64_t chunk = (int64_t)kThreads * kPer;
+  const int64_t n_chunks = (n + chunk - 1) / chunk;
+  for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    int own[kPer];
+    unsigned rank[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int64_t i = c * chunk + (int64_t)j * kThreads + threadIdx.x;
+      own[j] = -1;
+      if (i < n) {
+        own[j] = owner_of(keys[i], n_parts);
+        rank[j] = atomicAdd(&s_cnt[own[j]], 1u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < n_parts && s_cnt[threadIdx.x])
+      s_base[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int64_t i = c * chunk + (int64_t)j * kThreads + threadIdx.x;
+      if (own[j] >= 0) perm[s_base[own[j]] + rank[j]] = i;
+    }
+    __syncthreads();
   }
 }
 

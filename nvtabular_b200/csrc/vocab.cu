@@ -133,8 +133,9 @@ __device__ __forceinline__ void lookup_load(const Lookup& t, int64_t b, LProbe<N
 
 template <bool NARROW>
 __device__ __forceinline__ int64_t lookup_home(const Lookup& t, int64_t key) {
-  const uint64_t h = table_mix64((uint64_t)key);
-  return NARROW ? (int64_t)(h & (uint64_t)((t.capacity >> 2) - 1)) : (int64_t)(h & (uint64_t)(t.capacity - 1));
+  if constexpr (NARROW)
+    return (int64_t)((uint64_t)table_mix32((uint32_t)(int32_t)key) & (uint64_t)((t.capacity >> 2) - 1));
+  return (int64_t)(table_mix64((uint64_t)key) & (uint64_t)(t.capacity - 1));
 }
 
 // position of `key` or -1, starting from a prefetched first probe.  Single exit: the
@@ -385,7 +386,7 @@ lookup_build_any_kernel(const int64_t* __restrict__ keys, int64_t n, int64_t* sl
       // free slot of the home bucket, spilling to the following buckets
       const unsigned long long want = ((unsigned long long)(unsigned)(i + 1) << 32) | (unsigned)(int)k;
       const int64_t bmask = (capacity >> 2) - 1;
-      int64_t b = (int64_t)(table_mix64((uint64_t)k) & (uint64_t)bmask);
+      int64_t b = (int64_t)((uint64_t)table_mix32((uint32_t)(int32_t)k) & (uint64_t)bmask);
       bool placed = false;
       while (!placed) {
         for (int j = 0; j < 4 && !placed; ++j) placed = (atomicCAS(ns + 4 * b + j, 0ull, want) == 0ull);
@@ -510,7 +511,7 @@ small_vocab_kernel(const int64_t* __restrict__ keys_in, const int64_t* __restric
     if (narrow) {
       const unsigned long long want = ((unsigned long long)(unsigned)(i + 1) << 32) | (unsigned)(int)key;
       const long long bmask = (capacity >> 2) - 1;
-      long long b = (long long)(table_mix64((uint64_t)key) & (uint64_t)bmask);
+      long long b = (long long)((uint64_t)table_mix32((uint32_t)(int32_t)key) & (uint64_t)bmask);
       bool placed = false;
       while (!placed) {                                   // keys are distinct
         for (int j = 0; j < 4 && !placed; ++j) placed = (atomicCAS(ns + 4 * b + j, 0ull, want) == 0ull);

@@ -112,7 +112,7 @@ def global_merge(agg, engine=None):
     return all_k, all_s, all_v, int(ns.item()), nv
 
 
-def global_merge_many(aggs, engine=None):
+def global_merge_many(aggs, engine=None, owner_pool=None):
     """Cross-GPU merge of MANY keys-only tables (one per Categorify column) with a constant
     number of collectives: the per-column partials of all columns travel in ONE all-to-all
     (keys) + ONE (sizes), each owner merges its shard of every column, and the merged shards
@@ -121,9 +121,21 @@ def global_merge_many(aggs, engine=None):
     Returns [(keys, sizes, null_size)] per table, identical on every rank."""
     if engine is None:
         from . import engine
+    import os
+    import time
     import torch.distributed as dist
     w, rank = world()
+    trace = bool(os.environ.get("NVTB_TRACE")) and w > 1
+    marks = []
+
+    def mark(name):
+        if trace:
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
+    mark("start")
     exported = [a.export() for a in aggs]            # (keys, sizes, None, null_size, None)
+    mark("export")
     if w == 1:
         return [(k, s, ns) for (k, s, _, ns, _) in exported]
     nc = len(aggs)
@@ -142,8 +154,10 @@ def global_merge_many(aggs, engine=None):
             send_s[r][c] = gs[off: off + cnt[r]]
             counts[r, c] = cnt[r]
             off += cnt[r]
+    mark("partition")
     sk = torch.cat([t for r in range(w) for t in send_k[r]])
     ss = torch.cat([t for r in range(w) for t in send_s[r]])
+    mark("cat")
     # 2. exchange the count matrix, then keys and sizes
     cm_send = counts.to(dev).reshape(-1)
     cm_recv = torch.empty_like(cm_send)              # cm_recv[src, c] = rows src sends me for column c
@@ -155,6 +169,7 @@ def global_merge_many(aggs, engine=None):
     rs = torch.empty(sum(out_split), dtype=torch.int64, device=dev)
     dist.all_to_all_single(rk, sk, output_split_sizes=out_split, input_split_sizes=in_split)
     dist.all_to_all_single(rs, ss, output_split_sizes=out_split, input_split_sizes=in_split)
+    mark("all_to_all")
     # 3. owner merge per column (exact global sizes over disjoint keys)
     src_off = [0]
     for r in range(w):
@@ -168,11 +183,22 @@ def global_merge_many(aggs, engine=None):
             segs_k.append(rk[o: o + n])
             segs_s.append(rs[o: o + n])
         ck, cs = torch.cat(segs_k), torch.cat(segs_s)
-        owner = engine.HashAgg(0, capacity_hint=max(ck.numel(), 1))
+        # owner tables are pooled by the caller: creating a table (pinned mailbox, event,
+        # device counters) costs far more than merging a shard into it
+        if owner_pool is not None and c < len(owner_pool) and owner_pool[c] is not None:
+            owner = owner_pool[c]
+            owner.reset()
+        else:
+            owner = engine.HashAgg(0, capacity_hint=max(ck.numel(), 1))
+            if owner_pool is not None:
+                while len(owner_pool) <= c:
+                    owner_pool.append(None)
+                owner_pool[c] = owner
         owner.merge(ck, cs)
         ok, os_, _, _, _ = owner.export()
         owned_k.append(ok)
         owned_s.append(os_)
+    mark("owner_merge")
     # 4. all-gather the merged shards of all columns at once
     n_local = torch.tensor([t.numel() for t in owned_k], dtype=torch.int64, device=dev)
     n_all = torch.empty(w * nc, dtype=torch.int64, device=dev)
@@ -192,6 +218,7 @@ def global_merge_many(aggs, engine=None):
     ns = torch.tensor([e[3] for e in exported], dtype=torch.int64, device=dev)
     dist.all_reduce(ns, op=dist.ReduceOp.SUM)
     ns_h = ns.cpu().tolist()
+    mark("allgather")
     out = []
     for c in range(nc):
         ks, szs = [], []
@@ -201,4 +228,9 @@ def global_merge_many(aggs, engine=None):
             ks.append(gk[o: o + n])
             szs.append(gs[o: o + n])
         out.append((torch.cat(ks), torch.cat(szs), int(ns_h[c])))
+    mark("split")
+    if trace and rank == 0:
+        print("[nvtb trace] merge_many: " + ", ".join(
+            f"{marks[i][0]} {1e3 * (marks[i][1] - marks[i - 1][1]):.2f} ms" for i in range(1, len(marks)))
+              + f"; keys sent {sk.numel()}, owned {sum(t.numel() for t in owned_k)}", flush=True)
     return out

@@ -200,6 +200,7 @@ class Categorify(StatOperator):
         self._user_vocabs = vocabs
         self._aggs = {}      # storage name -> engine.HashAgg, reused (reset) across fits
         self._rows_seen = {}
+        self._owner_pool = []   # per-column owner tables of the cross-GPU merge, reused across fits
         self.vocabs = {}
         self.categories = _Categories()
         if vocabs is not None:
@@ -298,7 +299,7 @@ class Categorify(StatOperator):
                         self._insert(storage, agg, space.keys_for(part[n]))
                 part = next(it, None)
             from ..dist import global_merge_many
-            merged = global_merge_many([state[storage][1] for storage, _ in groups])
+            merged = global_merge_many([state[storage][1] for storage, _ in groups], owner_pool=self._owner_pool)
             return {storage: self._close_group(storage, [storage], state[storage][0], state[storage][1], m)
                     for (storage, names), m in zip(groups, merged)}
         parts = [first] + list(it)   # strings / general combos need a dictionary pre-pass

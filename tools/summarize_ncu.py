@@ -8,6 +8,37 @@ import csv
 import sys
 
 
+FAMILY = {"insert_keys_kernel": "hashagg_insert", "encode_kernel": "encode", "moments_kernel": "moments",
+          "transform_kernel": "normalize", "export_kernel": "hashagg_export"}
+
+
+def traffic_json(path, rows_per_gpu, skip_to_last_step=True):
+    """per-kernel-family average DRAM bytes per launch (for bench.py's roofline.traffic)"""
+    import json
+    with open(path) as f:
+        lines = [ln for ln in f if not ln.startswith("==")]
+    per_launch = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        key = (int(row["ID"]), row["Kernel Name"])
+        try:
+            per_launch.setdefault(key, {})[row["Metric Name"]] = float(row["Metric Value"].replace(",", ""))
+        except ValueError:
+            pass
+    items = list(per_launch.items())
+    if skip_to_last_step:
+        enc = [i for i, ((_, n), _) in enumerate(items) if "encode_kernel" in n]
+        if len(enc) >= 52:
+            items = items[enc[len(enc) - 27] + 2:]
+    out = {}
+    for pat, fam in FAMILY.items():
+        ms = [m for (_, n), m in items if pat in n]
+        if ms and "dram__bytes_read.sum" in ms[0]:
+            out[fam] = {"rows_per_gpu": rows_per_gpu, "launches": len(ms),
+                        "dram_bytes_per_launch": sum(m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"] for m in ms) / len(ms),
+                        "avg_launch_us": sum(m["gpu__time_duration.sum"] for m in ms) / len(ms) / 1e3}
+    return json.dumps(out, indent=1)
+
+
 def main(path):
     with open(path) as f:
         lines = [ln for ln in f if not ln.startswith("==")]
@@ -36,4 +67,7 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) > 3 and sys.argv[2] == "--traffic":
+        print(traffic_json(sys.argv[1], int(sys.argv[3])))
+    else:
+        main(sys.argv[1])
