@@ -271,6 +271,12 @@ def main():
         d["ms"] += s.elapsed_time(e)
         d["bytes"] += nbytes
         d["launches"] += 1
+    if os.environ.get("NVTB_BENCH_DUMP") and rank == 0:
+        per_step = len(prof) // max(1, args.steps)
+        for st in range(args.steps):
+            sys.stderr.write("[bench dump] step %d: %s\n" % (st, " ".join(
+                "%s:%.0f" % (f[:3] + f[-3:], s.elapsed_time(e) * 1e3)
+                for f, s, e, _ in prof[st * per_step:(st + 1) * per_step])))
     peak, peak_src = _peaks()
     kernels = {}
     for k, d in fam.items():

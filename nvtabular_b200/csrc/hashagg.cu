@@ -109,6 +109,7 @@ struct nvtb_hashagg {
   int64_t u_known;           // distinct keys at the last settle
   int64_t rows_total;        // rows folded in so far
   double k_est;              // cardinality estimate (0 = none yet)
+  double predicted;          // distinct keys expected after the batch being prepared
   int64_t hint;
   int n_agg;
   bool mailbox_valid;        // mailbox == device counters (no launch / host edit since the readback)
@@ -290,6 +291,10 @@ __global__ void special_init_kernel(Counters* ctr, double* special_vals, int n_a
       }
   }
 }
+
+}  // namespace nvtb
+#include "fold_i32.cuh"
+namespace nvtb {
 
 // ---------------------------------------------------------------------------
 // insert, keys only (Categorify)
@@ -1063,8 +1068,94 @@ static int prepare(nvtb_hashagg* h, int64_t rows, cudaStream_t st) {
     predicted = (double)h->u_known + (double)rows;   // no information: worst case
   }
   predicted = std::min(predicted, (double)h->u_known + (double)rows);
+  h->predicted = predicted;
   const int64_t want = next_pow2((int64_t)(2.5 * predicted) + 1);
   return grow_to(h, want, st);
+}
+
+struct PartScratch { void* ptr; size_t bytes; cudaEvent_t ev; cudaStream_t last; bool used; };
+static PartScratch g_part = {nullptr, 0, nullptr, nullptr, false};
+
+// int32 keys, narrow table, no payload: shared-memory fold, hash-partitioned first when the
+// expected number of distinct keys exceeds what one SM's shared memory holds (fold_i32.cuh)
+static int launch_fold_i32(nvtb_hashagg* h, const int32_t* kp, const uint8_t* mp, int64_t m,
+                           cudaStream_t st) {
+  static bool attrs = false;
+  constexpr int kDirectSmem = (int)(kFoldBucketsDirect * kFoldWays * kFoldSlotBytes);
+  constexpr int kPartsSmem = (int)(kFoldBucketsParts * kFoldWays * kFoldSlotBytes);
+  constexpr int kScatterSmemMax = kPartTile * 4 + 2 * 4 * kMaxParts;
+  if (!attrs) {
+    NVTB_CUDA_OK(cudaFuncSetAttribute(fold_i32_kernel<kFoldThreadsDirect, 1, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kDirectSmem));
+    NVTB_CUDA_OK(cudaFuncSetAttribute(fold_i32_kernel<kFoldThreadsParts, 2, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kPartsSmem));
+    NVTB_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmemMax));
+    attrs = true;
+  }
+  const int sms = sm_count();
+  const bool aligned = is_aligned32(kp);
+  // distinct keys this batch is expected to show (the table may already hold some of them)
+  const double fresh = std::min(h->predicted, (double)m);
+  const bool parts = aligned && m >= ((int64_t)1 << 18) && m < (int64_t)0xFFFF0000ll &&
+                     fresh > kFoldMaxLoad * (double)(kFoldWays * kFoldBucketsDirect);
+  if (!parts) {
+    constexpr int64_t kStep = (int64_t)kFoldThreadsDirect * 8;
+    int64_t units = std::min<int64_t>(sms, (m + kStep - 1) / kStep);
+    int64_t chunk = ((m + units - 1) / units + kStep - 1) / kStep * kStep;
+    units = (m + chunk - 1) / chunk;
+    fold_i32_kernel<kFoldThreadsDirect, 1, false><<<(int)units, kFoldThreadsDirect, kDirectSmem, st>>>(
+        kp, mp, m, nullptr, nullptr, (int)units, chunk, 0, kFoldBucketsDirect, aligned ? 1 : 0,
+        h->t, h->ctr, h->arena);
+    NVTB_LAUNCH_OK();
+    return NVTB_OK;
+  }
+  int lg = 9;
+  while ((1 << lg) < kMinParts) ++lg;
+  while ((1 << lg) < kMaxParts &&
+         fresh / (double)(1 << lg) > kFoldMaxLoad * (double)(kFoldWays * kFoldBucketsParts)) ++lg;
+  const int P = 1 << lg;
+  // partition buffer: ONE grow-only device allocation shared by every handle (a fresh
+  // 268 MB cudaMallocAsync per column occasionally costs tens of ms when the pool has to
+  // map new memory).  Uses are ordered by an event when the stream changes.
+  uint32_t* meta = nullptr;      // total[P] | starts[P] | cursor[P]
+  int32_t* buf = nullptr;
+  {
+    std::lock_guard<std::recursive_mutex> lk(g_arena_mu);
+    const size_t need = sizeof(uint32_t) * 3 * kMaxParts + sizeof(int32_t) * (size_t)(m + 8 * (int64_t)kMaxParts);
+    if (g_part.bytes < need) {
+      NVTB_CUDA_OK(cudaDeviceSynchronize());
+      if (g_part.ptr) cudaFree(g_part.ptr);
+      g_part.ptr = nullptr; g_part.bytes = 0;
+      NVTB_CUDA_OK(cudaMalloc(&g_part.ptr, need));
+      g_part.bytes = need;
+    }
+    if (g_part.ev == nullptr) NVTB_CUDA_OK(cudaEventCreateWithFlags(&g_part.ev, cudaEventDisableTiming));
+    if (g_part.used && g_part.last != st) NVTB_CUDA_OK(cudaStreamWaitEvent(st, g_part.ev, 0));
+    meta = reinterpret_cast<uint32_t*>(g_part.ptr);
+    buf = reinterpret_cast<int32_t*>(meta + 3 * kMaxParts);
+  }
+  NVTB_CUDA_OK(cudaMemsetAsync(meta, 0, sizeof(uint32_t) * P, st));
+  const int64_t tiles = (m + kPartTile - 1) / kPartTile;
+  part_hist_kernel<<<(int)std::min<int64_t>(tiles, 3 * sms), kPartThreads, 4 * P, st>>>(
+      kp, mp, m, lg, meta, h->ctr);
+  NVTB_LAUNCH_OK();
+  part_scan_kernel<<<1, kPartThreads, 0, st>>>(meta, lg, meta + P, meta + 2 * P);
+  NVTB_LAUNCH_OK();
+  part_scatter_kernel<<<(int)std::min<int64_t>(tiles, 2 * sms), kPartThreads, kPartTile * 4 + 2 * 4 * P, st>>>(
+      kp, mp, m, lg, meta + 2 * P, buf);
+  NVTB_LAUNCH_OK();
+  fold_i32_kernel<kFoldThreadsParts, 2, true><<<std::min(P, 2 * sms), kFoldThreadsParts, kPartsSmem, st>>>(
+      buf, nullptr, m + 8 * (int64_t)P, meta + P, meta + 2 * P, P, 0, lg, kFoldBucketsParts, 1,
+      h->t, h->ctr, h->arena);
+  NVTB_LAUNCH_OK();
+  {
+    std::lock_guard<std::recursive_mutex> lk(g_arena_mu);
+    NVTB_CUDA_OK(cudaEventRecord(g_part.ev, st));
+    g_part.used = true;
+    g_part.last = st;
+  }
+  return NVTB_OK;
 }
 
 template <typename KeyT>
@@ -1075,7 +1166,10 @@ static int launch_insert(nvtb_hashagg* h, const KeyT* kp, const uint8_t* mp, con
   const int64_t room = std::max<int64_t>(0, h->t.capacity / 2 - h->u_known);
   arm_launch_kernel<<<1, 1, 0, st>>>(h->ctr, (long long)room);
   NVTB_LAUNCH_OK();
-  if (h->n_agg == 0) {
+  if (h->n_agg == 0 && sizeof(KeyT) == 4 && h->t.narrow) {
+    rc = launch_fold_i32(h, reinterpret_cast<const int32_t*>(kp), mp, m, st);
+    if (rc) return rc;
+  } else if (h->n_agg == 0) {
     const int grid = scan_grid(m, kInsertCtasPerSm);
     const int64_t budget = 0;
     constexpr int kSmemBytes = SmemAgg<KeyT>::kBytes;

@@ -216,6 +216,58 @@ def test_hashagg_counts(eng, dtype, n, card):
     _agg_check(eng, arr, mask)
 
 
+def _fold_unhash(h):
+    """inverse of csrc/fold_i32.cuh fold_hash (the shared table never stores h = 0xFFFFFFFF)"""
+    M = 0xFFFFFFFF
+    h = (h * 0xA5CB9243) & M
+    h ^= h >> 15
+    h ^= h >> 30
+    return (h * 0x0E8B2F51) & M
+
+
+@pytest.mark.parametrize("n,card,hint", [
+    (1 << 22, 20_000, 0),          # direct mode, table close to full
+    (1 << 22, 40_000, 0),          # just above the direct capacity: partitioned
+    (1 << 22, 40_000, 5_000),      # hint far too low: direct mode, most rows miss shared memory
+    (3_000_001, 2_500_000, 0),     # partitioned, almost all distinct, ragged tail
+    (1 << 21, 300_000, 30_000_000),  # hint far too high: 4096 partitions
+    (300_000, 100_000, 0),         # below the partition threshold
+])
+def test_hashagg_int32_fold_paths(eng, n, card, hint):
+    rng = np.random.default_rng(n + card + hint)
+    ids = rng.integers(0, card, n)
+    arr = ((ids * 2654435761) % (1 << 32)).astype(np.uint32).view(np.int32)   # negative keys too
+    # the key whose shared-memory hash is the reserved value, INT32_MIN/MAX, 0 and -1
+    special = np.array([_fold_unhash(0xFFFFFFFF), 0x80000000, 0x7FFFFFFF, 0, 0xFFFFFFFF], dtype=np.uint32).view(np.int32)
+    arr[rng.integers(0, n, 5000)] = special[rng.integers(0, len(special), 5000)]
+    mask = rng.random(n) < 0.03
+    col = _col(arr, mask)
+    h = eng.HashAgg(0, capacity_hint=hint) if hint else eng.HashAgg(0)
+    h.insert(col)
+    keys, sizes, _, null_size, _ = h.export()
+    vc = pd.Series(arr[~mask]).value_counts().sort_index()
+    got = pd.Series(sizes.cpu().numpy(), index=keys.cpu().numpy()).sort_index()
+    assert null_size == int(mask.sum())
+    np.testing.assert_array_equal(got.index.to_numpy(), vc.index.to_numpy().astype(np.int64))
+    np.testing.assert_array_equal(got.to_numpy(), vc.to_numpy())
+
+
+def test_hashagg_int32_unaligned_slice(eng):
+    """a key column that does not start on a 32-byte boundary takes the scalar path"""
+    from nvtabular_b200.column import Column
+    rng = np.random.default_rng(5)
+    n = 700_001
+    arr = rng.integers(-50_000, 50_000, n).astype(np.int32)
+    full = _col(arr)
+    h = eng.HashAgg(0)
+    h.insert(Column(full.data[3:], None))
+    keys, sizes, _, null_size, _ = h.export()
+    vc = pd.Series(arr[3:]).value_counts().sort_index()
+    got = pd.Series(sizes.cpu().numpy(), index=keys.cpu().numpy()).sort_index()
+    np.testing.assert_array_equal(got.index.to_numpy(), vc.index.to_numpy().astype(np.int64))
+    np.testing.assert_array_equal(got.to_numpy(), vc.to_numpy())
+
+
 def test_hashagg_growth_and_batches(eng):
     """capacity grows several times; all distinct keys; multiple insert calls."""
     rng = np.random.default_rng(99)
