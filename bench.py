@@ -53,8 +53,11 @@ def _traffic(kernel, rows):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  ONE nvidia-smi
+    process, started before the warm-up (its start-up takes driver-wide locks for hundreds
+    of ms and would otherwise land inside a ~150 ms timed region) and left polling every
+    50 ms; stop(t0, t1) keeps the samples whose own timestamps fall inside the region."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -65,12 +68,20 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("NVTB_SMI_MS", "50"),
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def _epoch(stamp):
+        import datetime
+        try:
+            return datetime.datetime.strptime(stamp.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -79,20 +90,26 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                rows.append((self._epoch(f[0]), float(f[2]), float(f[3]), f[6:10]))
             except ValueError:
                 continue
-            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+        inside = [r for r in rows if t0 is not None and r[0] is not None and t0 - 0.05 <= r[0] <= t1 + 0.05]
+        window = "timed region"
+        if not inside:          # region shorter than the polling period: nearest samples
+            inside, window = rows[-3:], "nearest samples (region shorter than the 50 ms poll)"
+        sm, mx, reasons = [r[1] for r in inside], [r[2] for r in inside], set()
+        for r in inside:
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def build_workflow(nvt, out_path, int32_outputs=False):
@@ -236,14 +253,18 @@ def main():
         pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(35)
 
     # ---------------- device-resident timing --------------------------------------
+    sampler = ClockSampler(local_rank)
+    t_sampler = time.time()
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         out = run_step(nvt, wf, frame)
         del out
+    if rank == 0 and time.time() - t_sampler < 1.5:      # nvidia-smi start-up must be over
+        time.sleep(1.5 - (time.time() - t_sampler))
     sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     engine.profile = []
+    t_wall0 = time.time()
     launches0 = engine.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -254,7 +275,7 @@ def main():
     sync_all()
     prof = engine.profile
     engine.profile = None
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
     elapsed_ms = ev0.elapsed_time(ev1)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
