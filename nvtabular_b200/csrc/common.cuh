@@ -292,6 +292,31 @@ inline int scan_grid(int64_t n, int ctas_per_sm) {
 }
 
 // ---------------------------------------------------------------------------
+// shared-memory table hash (fold_i32.cuh, the shared-memory encode in vocab.cu): a
+// BIJECTION of the 32-bit key, so a shared table can store h instead of the key
+// ---------------------------------------------------------------------------
+constexpr uint32_t kFoldC1 = 0x9E3779B1u;
+constexpr uint32_t kFoldC2 = 0x85EBCA6Bu;
+constexpr uint32_t kFoldC1Inv = 0x0E8B2F51u;
+constexpr uint32_t kFoldC2Inv = 0xA5CB9243u;
+static_assert((uint32_t)(kFoldC1 * kFoldC1Inv) == 1u, "kFoldC1Inv");
+static_assert((uint32_t)(kFoldC2 * kFoldC2Inv) == 1u, "kFoldC2Inv");
+constexpr uint32_t kFoldEmpty = 0xFFFFFFFFu;   // the one h that is never stored in shared memory
+
+__host__ __device__ __forceinline__ uint32_t fold_hash(uint32_t k) {
+  uint32_t h = k * kFoldC1;
+  h ^= h >> 15;
+  return h * kFoldC2;
+}
+__host__ __device__ __forceinline__ uint32_t fold_unhash(uint32_t h) {
+  h *= kFoldC2Inv;
+  h ^= h >> 15;
+  h ^= h >> 30;
+  return h * kFoldC1Inv;
+}
+
+
+// ---------------------------------------------------------------------------
 // hashes
 // ---------------------------------------------------------------------------
 // (1) the reference-visible hash: pandas.util.hash_array on numeric data

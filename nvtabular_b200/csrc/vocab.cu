@@ -292,6 +292,107 @@ encode_kernel(const KeyT* __restrict__ keys, const uint8_t* __restrict__ mask,
 }
 
 // ---------------------------------------------------------------------------
+// encode with the vocabulary in SHARED memory (int32 keys, vocabularies of <= 14 336 keys:
+// 16 of the 26 Criteo columns).  A row of the global-lookup kernel above costs one random
+// 32-byte L2 sector (~150 G sectors/s on B200: >= 400 us per 2^26 rows, and every CTA
+// hammers the same few sectors when the vocabulary is tiny); here every CTA first builds
+// its own copy of the vocabulary as a 4-way-bucket table of h = fold_hash(key) (+ position)
+// in 224 KB of shared memory, and a row costs one LDS.128 + one LDS.32.  A key that found
+// its bucket full at build time is simply not in the shared copy: a row that meets a FULL
+// bucket without a match falls back to the global lookup, so the result never depends on
+// the build order.
+// ---------------------------------------------------------------------------
+constexpr int kEncSmemThreads = 1024;
+constexpr unsigned kEncSmemBuckets = 7168;                       // x 4 slots x 8 B = 224 KB
+constexpr int64_t kEncSmemMaxKeys = (int64_t)kEncSmemBuckets * 2;  // load <= 0.5
+
+static __device__ __noinline__ long long enc_fallback(const Lookup& t, int32_t key) {
+  return (long long)lookup_find(t, (int64_t)key);
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kEncSmemThreads, 1)
+encode_smem_kernel(const int32_t* __restrict__ keys, const uint8_t* __restrict__ mask, int64_t n,
+                   const int64_t* __restrict__ vkeys, int n_keep, Lookup t, EncodeParams p,
+                   HashCols hc, OutT* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* hk = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* ps = hk + 4 * kEncSmemBuckets;
+  constexpr unsigned nb = kEncSmemBuckets;
+  for (unsigned s = threadIdx.x; s < 4 * nb; s += kEncSmemThreads) hk[s] = kFoldEmpty;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_keep; i += kEncSmemThreads) {
+    const uint32_t h = fold_hash((uint32_t)(int32_t)vkeys[i]);
+    if (h == kFoldEmpty) continue;                 // reserved value: served by the fallback
+    const unsigned b = __umulhi(h, nb);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (atomicCAS(hk + 4 * b + j, kFoldEmpty, h) == kFoldEmpty) { ps[4 * b + j] = (uint32_t)i; break; }
+  }
+  __syncthreads();
+
+  auto label_of = [&](int64_t i, int32_t x, bool valid, long long pos) -> OutT {
+    if (!valid) return (OutT)p.null_label;
+    if (pos >= 0) return (OutT)(p.first_label + pos);
+    int64_t lab = p.oov_label;
+    if (p.num_buckets > 1) {
+      const uint64_t h = hc.ncols > 0 ? hash_cols_at(hc, i) : pandas_mix64(value_bits<int32_t>(x));
+      lab += (int64_t)(h % p.num_buckets);
+    }
+    return (OutT)lab;
+  };
+
+  constexpr int64_t step = (int64_t)kEncSmemThreads * 8;
+  for (int64_t base = (int64_t)blockIdx.x * step; base < n; base += (int64_t)gridDim.x * step) {
+    const int64_t i = base + (int64_t)threadIdx.x * 8;
+    if (i + 8 <= n) {
+      int32_t v[8];
+      ld_rows8<int32_t>(keys + i, v);
+      const unsigned m = valid8(mask, i);
+      OutT o[8];
+      unsigned pend = 0;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint4 c[4];
+        uint32_t h[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          h[k] = fold_hash((uint32_t)v[4 * half + k]);
+          const unsigned addr = (unsigned)__cvta_generic_to_shared(hk + 4 * __umulhi(h[k], nb));
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(c[k].x), "=r"(c[k].y), "=r"(c[k].z), "=r"(c[k].w) : "r"(addr));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = 4 * half + k;
+          const bool valid = (m >> r) & 1u;
+          const int j = (c[k].x == h[k]) ? 0 : (c[k].y == h[k]) ? 1 : (c[k].z == h[k]) ? 2 : (c[k].w == h[k]) ? 3 : -1;
+          long long pos = -1;
+          if (j >= 0 && h[k] != kFoldEmpty) {
+            pos = (long long)ps[4 * __umulhi(h[k], nb) + j];
+          } else if (valid && (c[k].w != kFoldEmpty || h[k] == kFoldEmpty)) {
+            pend |= 1u << r;                       // full bucket (slots fill in order) or reserved h
+          }
+          o[r] = label_of(i + r, v[r], valid, pos);
+        }
+      }
+      if (pend) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if ((pend >> r) & 1u) o[r] = label_of(i + r, v[r], true, enc_fallback(t, v[r]));
+      }
+      st_rows8<OutT>(out + i, o);
+    } else {
+      for (int64_t q = i; q < n; ++q) {
+        const bool valid = valid1(mask, q);
+        const int32_t x = keys[q];
+        out[q] = label_of(q, x, valid, valid ? (long long)lookup_find(t, (int64_t)x) : -1);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // group-statistics gather
 // ---------------------------------------------------------------------------
 constexpr int kMaxGatherCols = 16;
@@ -876,6 +977,23 @@ int nvtb_encode_apply(const nvtb_vocab_t* v, const nvtb_col_t* key, int64_t n,
   }
   EncodeParams p{null_label, oov_label, first_label, num_buckets};
   cudaStream_t st = (cudaStream_t)stream;
+  if (key->dtype == NVTB_I32 && v->t.narrow && v->info.n_kept > 0 && v->info.n_kept <= kEncSmemMaxKeys &&
+      n >= ((int64_t)1 << 18) && is_aligned32(key->data) && is_aligned32(out)) {
+    constexpr int kSmem = (int)(kEncSmemBuckets * 4 * 8);
+    constexpr int64_t kStep = (int64_t)kEncSmemThreads * 8;
+    const int g = (int)std::min<int64_t>(sm_count(), (n + kStep - 1) / kStep);
+    if (out_dtype == NVTB_I64) {
+      NVTB_CUDA_OK(cudaFuncSetAttribute(encode_smem_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      encode_smem_kernel<int64_t><<<g, kEncSmemThreads, kSmem, st>>>(
+          (const int32_t*)key->data, key->validity, n, v->keys, (int)v->info.n_kept, v->t, p, hc, (int64_t*)out);
+    } else {
+      NVTB_CUDA_OK(cudaFuncSetAttribute(encode_smem_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      encode_smem_kernel<int32_t><<<g, kEncSmemThreads, kSmem, st>>>(
+          (const int32_t*)key->data, key->validity, n, v->keys, (int)v->info.n_kept, v->t, p, hc, (int32_t*)out);
+    }
+    NVTB_LAUNCH_OK();
+    return NVTB_OK;
+  }
   const int grid = scan_grid(n, 8);
 #define NVTB_ENCODE(KT, OT)                                                                        \
   do {                                                                                             \
