@@ -444,6 +444,27 @@ xor_copy_kernel(const int64_t* src, int64_t* dst, int64_t n, long long mask) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i] ^ mask;
 }
 
+// 32-bit images for the radix sorts: int32-valued keys biased by 2^31 (unsigned order ==
+// signed order), sizes known to be < 2^32; and back
+__global__ void __launch_bounds__(kThreads)
+pack32_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes, int64_t n,
+              uint32_t* __restrict__ k32, uint32_t* __restrict__ s32) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    k32[i] = (uint32_t)keys[i] ^ 0x80000000u;
+    s32[i] = (uint32_t)sizes[i];
+  }
+}
+__global__ void __launch_bounds__(kThreads)
+unpack32_kernel(const uint32_t* __restrict__ k32, const uint32_t* __restrict__ s32, int64_t n,
+                int64_t* __restrict__ keys, int64_t* __restrict__ sizes) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    keys[i] = (int64_t)(int32_t)(k32[i] ^ 0x80000000u);
+    sizes[i] = (int64_t)s32[i];
+  }
+}
+
 // sums of the kept / all sizes, and "do the kept keys fit int32?"
 __global__ void __launch_bounds__(kThreads)
 vocab_scalars_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes,
@@ -834,6 +855,33 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* siz
       while (size_bits < 63 && ((int64_t)1 << size_bits) <= size_bound) ++size_bits;
     }
     const int g_x = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
+    if (key32 && size_bound > 0 && size_bound < ((int64_t)1 << 32)) {
+      // both sort keys fit 32 bits: sort (uint32, uint32) pairs - half the bytes per pass
+      uint32_t *a32 = nullptr, *b32 = nullptr, *c32 = nullptr, *d32 = nullptr;
+      NVTB_CUDA_OK(cudaMallocAsync(&a32, sizeof(uint32_t) * n, st));
+      NVTB_CUDA_OK(cudaMallocAsync(&b32, sizeof(uint32_t) * n, st));
+      NVTB_CUDA_OK(cudaMallocAsync(&c32, sizeof(uint32_t) * n, st));
+      NVTB_CUDA_OK(cudaMallocAsync(&d32, sizeof(uint32_t) * n, st));
+      pack32_kernel<<<g_x, kThreads, 0, st>>>(keys, sizes, n, a32, c32);
+      NVTB_LAUNCH_OK();
+      size_t ta = 0, tb = 0;
+      NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, ta, a32, b32, c32, d32, n, 0, 32, st));
+      NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, d32, c32, b32, a32, n, 0, size_bits, st));
+      size_t tbytes = std::max(ta, tb);
+      void* tmp32 = nullptr;
+      NVTB_CUDA_OK(cudaMallocAsync(&tmp32, tbytes ? tbytes : 1, st));
+      NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp32, tbytes, a32, b32, c32, d32, n, 0, 32, st));
+      NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(tmp32, tbytes, d32, c32, b32, a32, n, 0, size_bits, st));
+      unpack32_kernel<<<g_x, kThreads, 0, st>>>(a32, c32, n, k2, s2);
+      NVTB_LAUNCH_OK();
+      NVTB_CUDA_OK(cudaFreeAsync(a32, st));
+      NVTB_CUDA_OK(cudaFreeAsync(b32, st));
+      NVTB_CUDA_OK(cudaFreeAsync(c32, st));
+      NVTB_CUDA_OK(cudaFreeAsync(d32, st));
+      NVTB_CUDA_OK(cudaFreeAsync(tmp32, st));
+      NVTB_CUDA_OK(cudaFreeAsync(k1, st));
+      NVTB_CUDA_OK(cudaFreeAsync(s1, st));
+    } else {
     const int64_t* sort_in = keys;
     if (key32) {
       xor_copy_kernel<<<g_x, kThreads, 0, st>>>(keys, k2, n, 0x80000000ll);   // k2 is free until the 2nd sort
@@ -856,6 +904,7 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* siz
     NVTB_CUDA_OK(cudaFreeAsync(k1, st));
     NVTB_CUDA_OK(cudaFreeAsync(s1, st));
     NVTB_CUDA_OK(cudaFreeAsync(tmp, st));
+    }
     // the sorted arrays ARE the vocabulary (first n_keep rows); no second copy
     v->keys = k2;
     v->sizes = s2;
