@@ -18,6 +18,7 @@ def _leaf(col: Column) -> Column:
 
 
 class _MomentsOp(StatOperator):
+    fit_blocks_host = True      # fit ends with the moments read-back (Workflow.fit orders on this)
     fuses_fill = True
 
     def __init__(self, out_dtype=None):

@@ -104,6 +104,10 @@ class Workflow:
             ready = [n for n in stat_nodes if all(id(u) in fitted for u in upstream_stats(n))]
             if not ready:
                 raise RuntimeError("failed to find dependency-free StatOperator to fit")
+            # ops of one phase are independent: fit the ones whose fit ends in a blocking
+            # device->host read (Normalize's moments) FIRST, so that the read waits on an
+            # almost empty stream instead of draining everything Categorify has queued
+            ready.sort(key=lambda n: 0 if getattr(n.op, "fit_blocks_host", False) else 1)
             for n in ready:
                 stats = n.op.fit(n.input_columns, _UpstreamPartitions(dataset, n))
                 n.op.fit_finalize(stats)

@@ -73,7 +73,13 @@ def traffic_json(path, rows_per_gpu, n_cat_cols=26):
 def main(path):
     agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
     fam_ms = collections.defaultdict(float)
-    for (_, name), m in _launches(path):
+    items = _launches(path)
+    # the capture starts with bench.py generating the synthetic table (torch RNG / elementwise
+    # kernels): the bench steps begin at the first launch of one of the engine's kernels
+    first = next((i for i, ((_, n), _) in enumerate(items) if "nvtb::" in n), 0)
+    skipped = sum(m.get("gpu__time_duration.sum", 0.0) for _, m in items[:first])
+    items = items[first:]
+    for (_, name), m in items:
         fam_ms[_family(name) or "other"] += m.get("gpu__time_duration.sum", 0.0)
         short = name.split("(")[0].replace("void ", "")[:72]
         a = agg[short]
@@ -89,6 +95,7 @@ def main(path):
     print("\n| family (bench.py `kernels`) | total ms | share |\n|---|---:|---:|")
     for k, v in sorted(fam_ms.items(), key=lambda kv: -kv[1]):
         print(f"| {k} | {v / 1e6:.3f} | {100 * v / total:.1f}% |")
+    print(f"\n({first} launches / {skipped / 1e6:.1f} ms of synthetic-table generation before the first engine kernel are not listed)")
     print(f"\ntotal device time of the captured launches: {total / 1e6:.3f} ms "
           f"(cold-cache, serialised by ncu: compare SHARES, not absolutes)")
 
