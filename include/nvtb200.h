@@ -194,6 +194,12 @@ int nvtb_hashagg_export(nvtb_hashagg_t* h, int64_t* keys_out,
 int nvtb_partition_by_owner(const int64_t* keys, int64_t n, int n_parts,
                             int64_t* perm_out, int64_t* part_counts_host,
                             void* stream);
+/* same grouping without a host round trip: the per-owner row counts stay on the
+ * device (part_counts_dev, int64[n_parts]); nothing synchronises, so the 26
+ * columns of a Categorify fit are partitioned back to back and their counts read
+ * with ONE copy (nvtabular_b200/dist.py global_merge_many). */
+int nvtb_partition_by_owner_async(const int64_t* keys, int64_t n, int n_parts,
+                                  int64_t* perm_out, int64_t* part_counts_dev, void* stream);
 int nvtb_gather_i64(const int64_t* src, const int64_t* perm, int64_t n,
                     int64_t* dst, void* stream);
 int nvtb_gather_f64_rows(const double* src, const int64_t* perm, int64_t n,

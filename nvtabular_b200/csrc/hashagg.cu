@@ -795,6 +795,15 @@ owner_count_kernel(const int64_t* __restrict__ keys, int64_t n, int n_parts,
     atomicAdd(&counts[threadIdx.x], (unsigned long long)sc[threadIdx.x]);
 }
 
+// exclusive prefix of the per-owner counts -> write cursors (n_parts <= 64: one thread)
+__global__ void owner_prefix_kernel(const unsigned long long* __restrict__ counts, int n_parts,
+                                    unsigned long long* __restrict__ cursors) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long acc = 0;
+    for (int p = 0; p < n_parts; ++p) { cursors[p] = acc; acc += counts[p]; }
+  }
+}
+
 // scatter pass: each CTA ranks its chunk of rows per owner in shared memory and reserves
 // ONE contiguous range per owner with a single global atomic, instead of one global
 // atomic per row on only `n_parts` addresses (which serialised at ~1 row/ns).
@@ -1473,6 +1482,27 @@ int nvtb_partition_by_owner(const int64_t* keys, int64_t n, int n_parts,
   owner_scatter_kernel<<<grid, kThreads, 0, st>>>(keys, n, n_parts, d + 64, perm_out);
   NVTB_LAUNCH_OK();
   NVTB_CUDA_OK(cudaStreamSynchronize(st));  // `cur` is a host temporary
+  NVTB_CUDA_OK(cudaFreeAsync(d, st));
+  return NVTB_OK;
+}
+
+int nvtb_partition_by_owner_async(const int64_t* keys, int64_t n, int n_parts,
+                                  int64_t* perm_out, int64_t* part_counts_dev, void* stream) {
+  NVTB_REQUIRE(n >= 0 && n_parts >= 1 && n_parts <= 64, "n_parts must be in [1, 64]");
+  NVTB_REQUIRE(part_counts_dev != nullptr, "part_counts_dev is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  NVTB_CUDA_OK(cudaMemsetAsync(part_counts_dev, 0, sizeof(int64_t) * n_parts, st));
+  if (n == 0) return NVTB_OK;
+  NVTB_REQUIRE(keys != nullptr && perm_out != nullptr, "NULL keys/perm");
+  unsigned long long* d = nullptr;     // [64] write cursors
+  NVTB_CUDA_OK(cudaMallocAsync(&d, sizeof(unsigned long long) * 64, st));
+  const int grid = plain_grid(n);
+  owner_count_kernel<<<grid, kThreads, 0, st>>>(keys, n, n_parts, reinterpret_cast<unsigned long long*>(part_counts_dev));
+  NVTB_LAUNCH_OK();
+  owner_prefix_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const unsigned long long*>(part_counts_dev), n_parts, d);
+  NVTB_LAUNCH_OK();
+  owner_scatter_kernel<<<grid, kThreads, 0, st>>>(keys, n, n_parts, d, perm_out);
+  NVTB_LAUNCH_OK();
   NVTB_CUDA_OK(cudaFreeAsync(d, st));
   return NVTB_OK;
 }

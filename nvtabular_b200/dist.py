@@ -141,19 +141,30 @@ def global_merge_many(aggs, engine=None, owner_pool=None):
     nc = len(aggs)
     dev = exported[0][0].device
     # 1. group every column's rows by owner rank
+    # (no host round trip per column: counts stay on the device until all 26 are queued)
+    grouped = []
+    if hasattr(engine, "partition_by_owner_async"):
+        counts_dev = torch.zeros((nc, w), dtype=torch.int64, device=dev)
+        for c, (k, s, _, _, _) in enumerate(exported):
+            perm = engine.partition_by_owner_async(k, w, counts_dev[c])
+            grouped.append((engine.gather_i64(k, perm), engine.gather_i64(s, perm)))
+        counts_nc = counts_dev.cpu()
+    else:                                   # stand-in engines of the CPU tests
+        counts_nc = torch.zeros((nc, w), dtype=torch.int64)
+        for c, (k, s, _, _, _) in enumerate(exported):
+            perm, cnt = engine.partition_by_owner(k, w)
+            grouped.append((engine.gather_i64(k, perm), engine.gather_i64(s, perm)))
+            counts_nc[c] = torch.tensor(cnt, dtype=torch.int64)
     send_k = [[None] * nc for _ in range(w)]
     send_s = [[None] * nc for _ in range(w)]
-    counts = torch.zeros((w, nc), dtype=torch.int64)
-    for c, (k, s, _, _, _) in enumerate(exported):
-        perm, cnt = engine.partition_by_owner(k, w)
-        gk = engine.gather_i64(k, perm)
-        gs = engine.gather_i64(s, perm)
+    counts = counts_nc.t().contiguous()     # [owner rank, column]
+    for c, (gk, gs) in enumerate(grouped):
         off = 0
         for r in range(w):
-            send_k[r][c] = gk[off: off + cnt[r]]
-            send_s[r][c] = gs[off: off + cnt[r]]
-            counts[r, c] = cnt[r]
-            off += cnt[r]
+            n_rc = int(counts[r, c])
+            send_k[r][c] = gk[off: off + n_rc]
+            send_s[r][c] = gs[off: off + n_rc]
+            off += n_rc
     mark("partition")
     sk = torch.cat([t for r in range(w) for t in send_k[r]])
     ss = torch.cat([t for r in range(w) for t in send_s[r]])
@@ -174,7 +185,7 @@ def global_merge_many(aggs, engine=None, owner_pool=None):
     src_off = [0]
     for r in range(w):
         src_off.append(src_off[-1] + out_split[r])
-    owned_k, owned_s = [], []
+    owned_k, owned_s, owners = [], [], []
     for c in range(nc):
         segs_k, segs_s = [], []
         for r in range(w):
@@ -195,6 +206,10 @@ def global_merge_many(aggs, engine=None, owner_pool=None):
                     owner_pool.append(None)
                 owner_pool[c] = owner
         owner.merge(ck, cs)
+        owners.append(owner)
+    # exports in a second loop: an export needs the merged size on the host, i.e. a sync on
+    # that column's merge; issued right after each merge it would drain the stream 26 times
+    for owner in owners:
         ok, os_, _, _, _ = owner.export()
         owned_k.append(ok)
         owned_s.append(os_)

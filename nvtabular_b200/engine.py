@@ -308,6 +308,18 @@ def partition_by_owner(keys: torch.Tensor, n_parts: int):
     return perm, [int(c) for c in counts]
 
 
+def partition_by_owner_async(keys: torch.Tensor, n_parts: int, counts_out: torch.Tensor):
+    """-> perm int64[n]; the per-owner row counts go to `counts_out` (device int64[n_parts])
+    without a host round trip."""
+    lib = _lib.load()
+    n = keys.numel()
+    perm = torch.empty(n, dtype=torch.int64, device=keys.device)
+    _lib.check(lib.nvtb_partition_by_owner_async(_ptr(keys), n, n_parts, _ptr(perm), _ptr(counts_out),
+                                                 _lib.stream_ptr()))
+    _count(3)
+    return perm
+
+
 def gather_i64(src: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(perm.numel(), dtype=torch.int64, device=src.device)

@@ -200,6 +200,7 @@ class Categorify(StatOperator):
         self._user_vocabs = vocabs
         self._aggs = {}      # storage name -> engine.HashAgg, reused (reset) across fits
         self._rows_seen = {}
+        self._rows_bound_global = 0
         self._owner_pool = []   # per-column owner tables of the cross-GPU merge, reused across fits
         self.vocabs = {}
         self.categories = _Categories()
@@ -300,6 +301,7 @@ class Categorify(StatOperator):
                 part = next(it, None)
             from ..dist import global_merge_many
             merged = global_merge_many([state[storage][1] for storage, _ in groups], owner_pool=self._owner_pool)
+            self._rows_bound_global = _global_rows(max(self._rows_seen.values(), default=0))
             return {storage: self._close_group(storage, [storage], state[storage][0], state[storage][1], m)
                     for (storage, names), m in zip(groups, merged)}
         parts = [first] + list(it)   # strings / general combos need a dictionary pre-pass
@@ -332,7 +334,9 @@ class Categorify(StatOperator):
     def _size_bound(self, storage) -> int:
         """upper bound on any group's size (speed hint for the radix sort); unknown across GPUs"""
         from ..dist import world
-        return self._rows_seen.get(storage, 0) if world()[0] == 1 else 0
+        if world()[0] == 1:
+            return self._rows_seen.get(storage, 0)
+        return self._rows_bound_global            # 0 = unknown
 
     def _open_group(self, storage, names, df):
         space = KeySpace.for_columns([_leaf(df[n]) for n in names])
@@ -540,6 +544,19 @@ class Categorify(StatOperator):
     @property
     def output_dtype(self):
         return self.dtype or np.int64
+
+
+def _global_rows(local_rows: int) -> int:
+    """sum over ranks of the rows a rank folded in: an upper bound on any group's global size"""
+    from ..dist import world
+    if world()[0] == 1:
+        return int(local_rows)
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() and \
+        dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([int(local_rows)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item())
 
 
 def _parse_bytes(v):

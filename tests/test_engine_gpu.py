@@ -432,6 +432,14 @@ def test_partition_by_owner_and_pack(eng):
     for s in range(8):
         for k in set(g[bounds[s]:bounds[s + 1]].tolist()):
             assert seg_of.setdefault(k, s) == s
+    # the variant without a host round trip: same grouping contract, counts on the device
+    cd = torch.zeros(8, dtype=torch.int64, device="cuda")
+    perm2 = eng.partition_by_owner_async(keys, 8, cd)
+    assert cd.cpu().tolist() == counts
+    g2 = eng.gather_i64(keys, perm2).cpu().numpy()
+    assert sorted(perm2.cpu().tolist()) == list(range(100000))
+    for s in range(8):
+        assert set(g2[bounds[s]:bounds[s + 1]].tolist()) == set(g[bounds[s]:bounds[s + 1]].tolist())
     a = rng.integers(-100, 100, 1000).astype("int32")
     b = rng.integers(-100, 100, 1000).astype("int32")
     ma, mb = rng.random(1000) < 0.2, rng.random(1000) < 0.2
