@@ -6,28 +6,30 @@
 // into.  Design (B200-first, not a translation of cuDF's groupby, which sizes a
 // fresh 2N-slot table per partition):
 //
-//   * table slot = {int64 key, int64 size} (16 B, one 32-B sector holds two) in
-//     HBM/L2; optional per-slot payload {sum, sumsq, min, max} per cont column.
-//   * ONE launch per (column, batch).  The insert kernel streams the key column
-//     with 256-bit loads and first folds rows into a per-CTA shared-memory
-//     table (4096 slots, ATOMS), so hot keys (Zipf heads, low-cardinality
-//     columns) cost one global atomic per distinct key per CTA instead of one
-//     per row; a CTA whose first tile shows < 25 % reuse bypasses shared memory
-//     (high-cardinality columns) and goes straight to the global table
-//     (key CAS + RED.ADD on the size).
+//   * two slot layouts (see `struct Table`): wide {int64 key, int64 size} (+ optional
+//     per-slot payload {sum, sumsq, min, max} per cont column) and narrow 8-byte packed
+//     slots in 4-way sector buckets for int32 keys without payload.
+//   * int32 keys without payload (every Categorify column of the Criteo workload) take
+//     the path of fold_i32.cuh: rows are absorbed in SHARED memory (find-or-claim tables
+//     of 110-224 KB per CTA), after a one-pass hash partition of the column when the
+//     expected number of distinct keys exceeds what one table holds; the global table
+//     only sees one (key, count) pair per distinct key per CTA / partition.
+//   * other keys: ONE launch per (column, batch); insert_keys_kernel streams the key
+//     column with 256-bit loads and first folds rows into a per-CTA shared-memory table
+//     (64 KB) - a CTA whose first tile shows < 25 % reuse bypasses it; insert_agg_kernel
+//     (payload) updates the global table row by row.
 //   * the table is sized from a CARDINALITY ESTIMATE (exact distinct count of
 //     the first 2^20 rows, inverted through U = K(1 - exp(-s/K)), or the
 //     caller's hint), not from the worst case.  Correctness never depends on
-//     the estimate: a thread may add at most `budget` new keys per launch
-//     (keeps the load factor <= 0.5) and gives up after 128 probes; a refused
+//     the estimate: a probe gives up after 128 buckets and the refused
 //     (key, count) pair goes to an overflow ARENA sized for the launch.  The
 //     next call on the handle ("settle") reads the counters back, grows the
 //     table if the arena is non-empty and merges the arena into it.
 //   * the null key (dropna=False) and the one key equal to the EMPTY sentinel
 //     (INT64_MIN) live in two "special" groups outside the table.
 //
-// Throughput bound: shared/L2 atomic units and random 32-B sector traffic, not
-// the HBM stream; see DESIGN.md "K3 roofline".
+// Throughput bound: the shared-memory pipe and L2 atomics / random 32-B sector traffic,
+// not the HBM stream; see DESIGN.md "K3 design and its real roofline".
 #include <algorithm>
 #include <mutex>
 #include <new>
@@ -84,7 +86,7 @@ struct Counters {
   unsigned long long n_unique;   // distinct keys in the table
   unsigned long long size[2];    // special groups: [0] null key, [1] INT64_MIN key
   unsigned long long ovf_count;  // pairs refused into the arena by the pending launch
-  long long budget;              // new keys the current launch may still claim (load <= 0.5)
+  long long reserved;
 };
 
 struct Arena {
@@ -274,14 +276,13 @@ __global__ void table_init_kernel(Table t) {
   }
 }
 
-__global__ void arm_launch_kernel(Counters* ctr, long long budget) {
+__global__ void arm_launch_kernel(Counters* ctr) {
   ctr->ovf_count = 0ull;
-  ctr->budget = budget;
 }
 
 __global__ void special_init_kernel(Counters* ctr, double* special_vals, int n_agg) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    ctr->n_unique = 0; ctr->size[0] = 0; ctr->size[1] = 0; ctr->ovf_count = 0; ctr->budget = 0;
+    ctr->n_unique = 0; ctr->size[0] = 0; ctr->size[1] = 0; ctr->ovf_count = 0; ctr->reserved = 0;
     for (int g = 0; g < 2; ++g)
       for (int j = 0; j < n_agg; ++j) {
         double* v = special_vals + (g * n_agg + j) * 4;
@@ -406,7 +407,7 @@ template <typename KeyT, bool NARROW>
 __global__ void __launch_bounds__(kThreads, 3)
 insert_keys_kernel(const KeyT* __restrict__ keys,
                    const uint8_t* __restrict__ mask, int64_t n, Table t,
-                   Counters* ctr, Arena arena, int64_t /*unused*/) {
+                   Counters* ctr, Arena arena) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemAgg<KeyT> sm(smem_raw);
   __shared__ unsigned long long s_null, s_min;
@@ -552,10 +553,8 @@ template <typename KeyT>
 __global__ void __launch_bounds__(kThreads)
 insert_agg_kernel(const KeyT* __restrict__ keys,
                   const uint8_t* __restrict__ mask, AggCols agg, int64_t n,
-                  Table t, Counters* ctr, double* special_vals, Arena arena,
-                  int64_t thread_budget) {
+                  Table t, Counters* ctr, double* special_vals, Arena arena) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  (void)thread_budget;
   unsigned n_new = 0;
   const double nan = __longlong_as_double(0x7FF8000000000000ll);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -601,9 +600,8 @@ template <bool NARROW>
 __global__ void __launch_bounds__(kThreads)
 merge_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes,
              const double* __restrict__ vals, int64_t n, Table t, Counters* ctr,
-             double* special_vals, Arena arena, int64_t thread_budget) {
+             double* special_vals, Arena arena) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  (void)thread_budget;
   unsigned n_new = 0;
   // four rows per thread per step: their first probes are issued back to back
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
@@ -1031,14 +1029,12 @@ static int grow_to(nvtb_hashagg* h, int64_t new_cap, cudaStream_t st, bool force
 static int launch_merge(nvtb_hashagg* h, const int64_t* keys, const int64_t* sizes,
                         const double* vals, int64_t n, const Arena& arena, cudaStream_t st) {
   const int grid = plain_grid(n);
-  const int64_t room = std::max<int64_t>(0, h->t.capacity / 2 - h->u_known);
-  const int64_t budget = 0;
-  arm_launch_kernel<<<1, 1, 0, st>>>(h->ctr, (long long)room);
+  arm_launch_kernel<<<1, 1, 0, st>>>(h->ctr);
   NVTB_LAUNCH_OK();
   if (h->t.narrow)
-    merge_kernel<true><<<grid, kThreads, 0, st>>>(keys, sizes, vals, n, h->t, h->ctr, h->special_vals, arena, budget);
+    merge_kernel<true><<<grid, kThreads, 0, st>>>(keys, sizes, vals, n, h->t, h->ctr, h->special_vals, arena);
   else
-    merge_kernel<false><<<grid, kThreads, 0, st>>>(keys, sizes, vals, n, h->t, h->ctr, h->special_vals, arena, budget);
+    merge_kernel<false><<<grid, kThreads, 0, st>>>(keys, sizes, vals, n, h->t, h->ctr, h->special_vals, arena);
   NVTB_LAUNCH_OK();
   return NVTB_OK;
 }
@@ -1061,7 +1057,7 @@ static int settle(nvtb_hashagg* h) {
       // every refused pair may be a new key: size for all of them at load <= 0.25
       int rc = grow_to(h, next_pow2(4 * (h->u_known + ovf)), st);
       if (rc) return rc;
-      // budget: capacity/2 - u_known >= u_known + 2*ovf; a pair that is still refused (128
+      // a pair that is still refused (128
       // probes) lands in a fresh private arena and is settled by the loop
       rc = arena_alloc(&h->arena, ovf, h->n_agg, st);
       if (rc) return rc;
@@ -1197,30 +1193,27 @@ static int launch_insert(nvtb_hashagg* h, const KeyT* kp, const uint8_t* mp, con
                          int64_t m, cudaStream_t st) {
   int rc = arena_acquire(h, &h->arena, m, h->n_agg);
   if (rc) return rc;
-  const int64_t room = std::max<int64_t>(0, h->t.capacity / 2 - h->u_known);
-  arm_launch_kernel<<<1, 1, 0, st>>>(h->ctr, (long long)room);
+  arm_launch_kernel<<<1, 1, 0, st>>>(h->ctr);
   NVTB_LAUNCH_OK();
   if (h->n_agg == 0 && sizeof(KeyT) == 4 && h->t.narrow) {
     rc = launch_fold_i32(h, reinterpret_cast<const int32_t*>(kp), mp, m, st);
     if (rc) return rc;
   } else if (h->n_agg == 0) {
     const int grid = scan_grid(m, kInsertCtasPerSm);
-    const int64_t budget = 0;
     constexpr int kSmemBytes = SmemAgg<KeyT>::kBytes;
     if (h->t.narrow) {
       NVTB_CUDA_OK(cudaFuncSetAttribute(insert_keys_kernel<KeyT, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      insert_keys_kernel<KeyT, true><<<grid, kThreads, kSmemBytes, st>>>(kp, mp, m, h->t, h->ctr, h->arena, budget);
+      insert_keys_kernel<KeyT, true><<<grid, kThreads, kSmemBytes, st>>>(kp, mp, m, h->t, h->ctr, h->arena);
     } else {
       NVTB_CUDA_OK(cudaFuncSetAttribute(insert_keys_kernel<KeyT, false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      insert_keys_kernel<KeyT, false><<<grid, kThreads, kSmemBytes, st>>>(kp, mp, m, h->t, h->ctr, h->arena, budget);
+      insert_keys_kernel<KeyT, false><<<grid, kThreads, kSmemBytes, st>>>(kp, mp, m, h->t, h->ctr, h->arena);
     }
   } else {
     const int grid = plain_grid(m);
-    const int64_t budget = 0;
     insert_agg_kernel<KeyT><<<grid, kThreads, 0, st>>>(kp, mp, ac, m, h->t, h->ctr,
-                                                       h->special_vals, h->arena, budget);
+                                                       h->special_vals, h->arena);
   }
   NVTB_LAUNCH_OK();
   h->rows_total += m;

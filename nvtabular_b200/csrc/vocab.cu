@@ -225,8 +225,25 @@ struct EncodeParams {
   uint64_t num_buckets;  // <= 1: single OOV index
 };
 
+// label of one row from scratch: full lookup + OOV hashing.  Out of line on purpose: the
+// 16-row-unrolled fast paths below only FLAG the rows that need it (continued probing, OOV
+// hash buckets), which keeps them ~3x smaller (the fully inlined version spent a quarter
+// of its issue slots waiting for instructions, profiles/ncu_r1_encode_kernels.md).
+template <typename KeyT>
+static __device__ __noinline__ long long encode_slow(const Lookup& t, const EncodeParams& p,
+                                                     const HashCols& hc, int64_t i, KeyT x) {
+  const int64_t pos = lookup_find(t, (int64_t)x);
+  if (pos >= 0) return (long long)(p.first_label + pos);
+  int64_t lab = p.oov_label;
+  if (p.num_buckets > 1) {
+    const uint64_t h = hc.ncols > 0 ? hash_cols_at(hc, i) : pandas_mix64(value_bits<KeyT>(x));
+    lab += (int64_t)(h % p.num_buckets);
+  }
+  return (long long)lab;
+}
+
 template <typename KeyT, typename OutT, bool NARROW>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 encode_kernel(const KeyT* __restrict__ keys, const uint8_t* __restrict__ mask,
               int64_t n, Lookup t, EncodeParams p, HashCols hc,
               OutT* __restrict__ out) {
@@ -234,16 +251,8 @@ encode_kernel(const KeyT* __restrict__ keys, const uint8_t* __restrict__ mask,
   auto in_range = [](long long k) -> bool {
     return !NARROW || (k >= (long long)INT32_MIN && k <= (long long)INT32_MAX);
   };
-  auto label_of = [&](int64_t i, KeyT x, bool valid, int64_t pos) -> OutT {
-    if (!valid) return (OutT)p.null_label;
-    if (pos >= 0) return (OutT)(p.first_label + pos);
-    int64_t lab = p.oov_label;
-    if (p.num_buckets > 1) {
-      const uint64_t h = hc.ncols > 0 ? hash_cols_at(hc, i) : pandas_mix64(value_bits<KeyT>(x));
-      lab += (int64_t)(h % p.num_buckets);
-    }
-    return (OutT)lab;
-  };
+  const long long fl1 = (long long)p.first_label - 1;     // label = fl1 + (pos + 1)
+  const bool hash_oov = p.num_buckets > 1;
   const int64_t n_tiles = (n + kTile - 1) / kTile;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * kTile;
@@ -259,11 +268,12 @@ encode_kernel(const KeyT* __restrict__ keys, const uint8_t* __restrict__ mask,
 #pragma unroll
       for (int g = 0; g < kGroups; ++g) {
         const int64_t i = base + (int64_t)g * (kThreads * kRows) + (int64_t)threadIdx.x * kRows;
-        // per half of 4 rows: (1) first-probe sector loads back to back, (2) resolve;
-        // then one 256-bit store (two for 8-byte labels) of the 8 labels
+        // per half of 4 rows: (1) first-probe sector loads back to back, (2) resolve what the
+        // first bucket decides, flag the rest; then one 256-bit store (two for 8-byte labels)
         OutT o[kRows];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
+          unsigned pend = 0;
           LProbe<NARROW> pr[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -273,19 +283,55 @@ encode_kernel(const KeyT* __restrict__ keys, const uint8_t* __restrict__ mask,
             const int r = 4 * half + k;
             const bool valid = (m[g] >> r) & 1u;
             const long long key = (long long)v[g][r];
-            int64_t pos = -1;
-            if (valid && in_range(key)) pos = lookup_resolve<NARROW>(t, key, pr[k]);
-            o[r] = label_of(i + r, v[g][r], valid, pos);
+            long long lab = (long long)p.oov_label;
+            bool decided;
+            if constexpr (NARROW) {
+              // slot = ((pos + 1) << 32) | key; a free slot has pos + 1 == 0, so "low word
+              // equals the key" needs no separate emptiness test
+              unsigned pos1 = 0, hi_and = 0xFFFFFFFFu;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const unsigned lo = (unsigned)pr[k].w[j], hi = (unsigned)(pr[k].w[j] >> 32);
+                pos1 |= (lo == (unsigned)key) ? hi : 0u;
+                hi_and = (hi == 0u) ? 0u : hi_and;
+              }
+              if (sizeof(KeyT) == 8 && !in_range(key)) pos1 = 0u;    // cannot be in a narrow table
+              if (pos1) lab = fl1 + (long long)pos1;
+              // not found: final only if the bucket has a free slot (else the probe goes on)
+              decided = pos1 != 0u || ((hi_and == 0u || (sizeof(KeyT) == 8 && !in_range(key))) && !hash_oov);
+            } else {
+              decided = false;
+              if (key != kEmptyKey && pr[k].k == key) { lab = fl1 + 1 + (long long)pr[k].v; decided = true; }
+              else if (key != kEmptyKey && pr[k].k == kEmptyKey && !hash_oov) decided = true;
+            }
+            if (!valid) { lab = (long long)p.null_label; decided = true; }
+            if (!decided) pend |= 1u << r;
+            o[r] = (OutT)lab;
+          }
+          if (pend) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if ((pend >> (4 * half + k)) & 1u)
+                o[4 * half + k] = (OutT)encode_slow<KeyT>(t, p, hc, i + 4 * half + k, v[g][4 * half + k]);
+          }
+          if constexpr (sizeof(OutT) == 8) {      // 4 labels = one 256-bit store; frees their registers
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              w[2 * k] = (uint32_t)(uint64_t)o[4 * half + k];
+              w[2 * k + 1] = (uint32_t)((uint64_t)o[4 * half + k] >> 32);
+            }
+            st256(out + i + 4 * half, w);
           }
         }
-        st_rows8<OutT>(out + i, o);
+        if constexpr (sizeof(OutT) != 8)
+          st_rows8<OutT>(out + i, o);
       }
     } else {
       const int64_t end = (base + kTile < n) ? base + kTile : n;
       for (int64_t i = base + threadIdx.x; i < end; i += kThreads) {
-        const bool valid = valid1(mask, i);
         const KeyT x = keys[i];
-        out[i] = label_of(i, x, valid, valid ? lookup_find(t, (int64_t)x) : -1);
+        out[i] = valid1(mask, i) ? (OutT)encode_slow<KeyT>(t, p, hc, i, x) : (OutT)p.null_label;
       }
     }
   }
@@ -305,10 +351,6 @@ encode_kernel(const KeyT* __restrict__ keys, const uint8_t* __restrict__ mask,
 constexpr int kEncSmemThreads = 1024;
 constexpr unsigned kEncSmemBuckets = 7168;                       // x 4 slots x 8 B = 224 KB
 constexpr int64_t kEncSmemMaxKeys = (int64_t)kEncSmemBuckets * 2;  // load <= 0.5
-
-static __device__ __noinline__ long long enc_fallback(const Lookup& t, int32_t key) {
-  return (long long)lookup_find(t, (int64_t)key);
-}
 
 template <typename OutT>
 __global__ void __launch_bounds__(kEncSmemThreads, 1)
@@ -331,16 +373,8 @@ encode_smem_kernel(const int32_t* __restrict__ keys, const uint8_t* __restrict__
   }
   __syncthreads();
 
-  auto label_of = [&](int64_t i, int32_t x, bool valid, long long pos) -> OutT {
-    if (!valid) return (OutT)p.null_label;
-    if (pos >= 0) return (OutT)(p.first_label + pos);
-    int64_t lab = p.oov_label;
-    if (p.num_buckets > 1) {
-      const uint64_t h = hc.ncols > 0 ? hash_cols_at(hc, i) : pandas_mix64(value_bits<int32_t>(x));
-      lab += (int64_t)(h % p.num_buckets);
-    }
-    return (OutT)lab;
-  };
+  const long long fl = (long long)p.first_label;
+  const bool hash_oov = p.num_buckets > 1;
 
   constexpr int64_t step = (int64_t)kEncSmemThreads * 8;
   for (int64_t base = (int64_t)blockIdx.x * step; base < n; base += (int64_t)gridDim.x * step) {
@@ -367,27 +401,28 @@ encode_smem_kernel(const int32_t* __restrict__ keys, const uint8_t* __restrict__
           const int r = 4 * half + k;
           const bool valid = (m >> r) & 1u;
           const int j = (c[k].x == h[k]) ? 0 : (c[k].y == h[k]) ? 1 : (c[k].z == h[k]) ? 2 : (c[k].w == h[k]) ? 3 : -1;
-          long long pos = -1;
+          long long lab = (long long)p.oov_label;
+          bool decided = !hash_oov;              // a miss in a non-full bucket is OOV
           if (j >= 0 && h[k] != kFoldEmpty) {
-            pos = (long long)ps[4 * __umulhi(h[k], nb) + j];
-          } else if (valid && (c[k].w != kFoldEmpty || h[k] == kFoldEmpty)) {
-            pend |= 1u << r;                       // full bucket (slots fill in order) or reserved h
+            lab = fl + (long long)ps[4 * __umulhi(h[k], nb) + j];
+            decided = true;
+          } else if (c[k].w != kFoldEmpty || h[k] == kFoldEmpty) {
+            decided = false;                     // full bucket (slots fill in order) or reserved h
           }
-          o[r] = label_of(i + r, v[r], valid, pos);
+          if (!valid) { lab = (long long)p.null_label; decided = true; }
+          if (!decided) pend |= 1u << r;
+          o[r] = (OutT)lab;
         }
       }
       if (pend) {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
-          if ((pend >> r) & 1u) o[r] = label_of(i + r, v[r], true, enc_fallback(t, v[r]));
+          if ((pend >> r) & 1u) o[r] = (OutT)encode_slow<int32_t>(t, p, hc, i + r, v[r]);
       }
       st_rows8<OutT>(out + i, o);
     } else {
-      for (int64_t q = i; q < n; ++q) {
-        const bool valid = valid1(mask, q);
-        const int32_t x = keys[q];
-        out[q] = label_of(q, x, valid, valid ? (long long)lookup_find(t, (int64_t)x) : -1);
-      }
+      for (int64_t q = i; q < n; ++q)
+        out[q] = valid1(mask, q) ? (OutT)encode_slow<int32_t>(t, p, hc, q, keys[q]) : (OutT)p.null_label;
     }
   }
 }
