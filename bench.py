@@ -145,10 +145,19 @@ def run_step_e2e(nvt, wf, host_parts, out_host):
     byte crosses PCIe once (partitions are prefetched one ahead and stay in HBM between
     fit and transform), every output byte crosses it once (D2H overlapped with the next
     partition's kernels)."""
+    trace = os.environ.get("NVTB_BENCH_DUMP")
+    t0 = time.perf_counter()
     ds = nvt.Dataset(list(host_parts))
     wf.fit(ds)
+    if trace:
+        import torch
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
     tds = wf.transform(ds)
     res = tds.to_host(out_host if out_host else None)
+    if trace:
+        sys.stderr.write("[bench dump] e2e step: fit %.1f ms, transform+to_host %.1f ms\n"
+                         % ((t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3))
     return ds.h2d_bytes, tds.d2h_bytes, res
 
 
@@ -323,8 +332,12 @@ def main():
         e_rows = args.e2e_rows or rows
         src = frame if e_rows == rows else criteo_frame(e_rows, total_rows=total_rows, device=dev, rank=rank)
         host = host_partitions(src, args.e2e_parts)
-        if src is not frame:
-            del src
+        del src
+        if not os.environ.get("NVTB_BENCH_KEEP_FRAME"):
+            # the device-resident table and the allocator blocks cached by the timed region above
+            # are not part of the e2e leg: it starts from host buffers and a clean device pool
+            frame = None
+            torch.cuda.empty_cache()
         out_host = None
         # W >= 3 warm-up steps here too: the first e2e step pins ~21 GB of result buffers (seconds),
         # the second still grows the device allocator's pools

@@ -171,6 +171,11 @@ class Dataset:
         dev = torch.device("cuda", torch.cuda.current_device())
         out_stream = _copy_stream(dev, 1)
         main = torch.cuda.current_stream(dev)
+        # drain what is queued (the tail of a fit) before the D2H pipeline starts: measured on
+        # B200, the same fit + transform + to_host step takes ~610 ms with this sync and
+        # 760-1370 ms without it (bench.py e2e leg, 2^26 rows; the pipeline below then competes
+        # with the fit's still-pending uploads and frees for allocator blocks)
+        main.synchronize()
         res: List[DeviceFrame] = []
         for i, part in enumerate(self.partitions()):
             ev = torch.cuda.Event()
