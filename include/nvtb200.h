@@ -163,8 +163,11 @@ int nvtb_hashagg_destroy(nvtb_hashagg_t* h);
 /* empty the table but keep its capacity and cardinality estimate (a second fit
  * over similar data then needs neither growth nor the sampling pass) */
 int nvtb_hashagg_reset(nvtb_hashagg_t* h, void* stream);
-/* insert one batch of raw rows (one kernel launch); agg_cols_host may be NULL
- * when n_agg == 0.  Waits for the handle's PREVIOUS launch (its counters are
+/* insert one batch of raw rows; agg_cols_host may be NULL when n_agg == 0.
+ * int32 keys without payload are folded in SHARED memory (one kernel), after a
+ * one-pass hash partition of the column (three more kernels) when the expected
+ * number of distinct keys exceeds what one SM's shared memory holds
+ * (csrc/fold_i32.cuh); other keys take one kernel that updates the table directly.  Waits for the handle's PREVIOUS launch (its counters are
  * read back), never for the one it enqueues. */
 int nvtb_hashagg_insert(nvtb_hashagg_t* h, const nvtb_col_t* key_host,
                         const nvtb_col_t* agg_cols_host, int64_t n,
