@@ -356,8 +356,8 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_ms = float(t.item()) / e_steps
-        e2e = {"value": e_rows * world / (e_ms / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": e_ms, "rows_per_step": e_rows * world,
+        e2e = {"value": e_rows * world / (e_ms / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": e_ms, "rows_per_step": e_rows * world,
                "host_partitions": len(host),
                "warmup": max(3, args.warmup), "steps": e_steps,
                # fit needs every partition before the first label exists, so H2D and D2H of one

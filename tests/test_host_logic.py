@@ -151,3 +151,64 @@ def test_keyspace_string_and_float_keys_are_order_preserving():
     key = _float_to_key(Column(torch.from_numpy(x))).data.numpy()
     assert (np.diff(key) >= 0).all() and key[2] == key[3]
     np.testing.assert_array_equal(_key_to_float(key), np.where(x == 0, 0.0, x))
+
+
+def test_fold_hash_is_a_bijection_with_the_documented_inverse():
+    """csrc/common.cuh fold_hash / fold_unhash: the shared-memory tables of the group-by and
+    the encode store h = fold_hash(key) and recover the key with the inverse.  The constants
+    are read from the header; the arithmetic is restated here."""
+    src = open(os.path.join(ROOT, "nvtabular_b200", "csrc", "common.cuh")).read()
+    c = {k: int(v, 16) for k, v in re.findall(r"constexpr uint32_t (kFold\w+) = (0x[0-9A-Fa-f]+)u;", src)}
+    M = 0xFFFFFFFF
+    assert (c["kFoldC1"] * c["kFoldC1Inv"]) & M == 1 and (c["kFoldC2"] * c["kFoldC2Inv"]) & M == 1
+    assert c["kFoldC1"] & 1 and c["kFoldC2"] & 1
+
+    def fold_hash(k):
+        h = (k * c["kFoldC1"]) & M
+        h ^= h >> 15
+        return (h * c["kFoldC2"]) & M
+
+    def fold_unhash(h):
+        h = (h * c["kFoldC2Inv"]) & M
+        h ^= h >> 15
+        h ^= h >> 30
+        return (h * c["kFoldC1Inv"]) & M
+
+    rng = np.random.default_rng(3)
+    keys = [0, 1, M, 0x80000000, 0x7FFFFFFF] + [int(x) for x in rng.integers(0, 1 << 32, 20000)]
+    hs = [fold_hash(k) for k in keys]
+    assert [fold_unhash(h) for h in hs] == keys
+    assert len(set(hs)) == len(set(keys))
+    # exactly one key maps to the value the shared tables reserve for "empty"
+    assert fold_hash(fold_unhash(c["kFoldEmpty"])) == c["kFoldEmpty"]
+    # the partition digit (top bits) spreads sequential ids: no partition of 1024 gets > 2x its share
+    top = np.bincount([fold_hash(k) >> 22 for k in range(200000)], minlength=1024)
+    assert top.max() < 2 * 200000 / 1024
+
+
+def test_workflow_fits_host_blocking_ops_first(monkeypatch):
+    """ops of one phase are independent; the ones whose fit ends in a blocking device->host read
+    (Normalize's moments) are fitted first so that the read does not drain Categorify's queue"""
+    import nvtabular_b200 as nvt
+    from nvtabular_b200 import ops
+    order = []
+    for cls in (ops.Categorify, ops.Normalize):
+        monkeypatch.setattr(cls, "fit", lambda self, cols, ddf, _n=cls.__name__: order.append(_n) or {})
+        monkeypatch.setattr(cls, "fit_finalize", lambda self, stats: None)
+    monkeypatch.setattr(nvt.Workflow, "fit_schema", lambda self, schema: self)
+    wf = nvt.Workflow((["c"] >> ops.Categorify()) + (["x"] >> ops.FillMissing() >> ops.Normalize()))
+
+    class _DS:
+        schema = None
+    wf.fit(_DS())
+    assert order == ["Normalize", "Categorify"]
+
+
+def test_bench_clock_sampler_window():
+    """bench.py keeps the nvidia-smi samples whose own timestamps fall inside the timed region"""
+    sys.path.insert(0, ROOT)
+    import bench
+    import datetime
+    t = datetime.datetime(2026, 1, 2, 3, 4, 5, 250000)
+    assert abs(bench.ClockSampler._epoch(t.strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]) - t.timestamp()) < 1e-3
+    assert bench.ClockSampler._epoch("garbage") is None
