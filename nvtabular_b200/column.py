@@ -226,6 +226,100 @@ class Column:
         return cls.from_strings(vals, device)
 
     @classmethod
+    def from_arrow(cls, arr, device=None, pin=False) -> "Column":
+        """pyarrow Array / ChunkedArray -> Column without going through pandas: the Arrow
+        validity bitmap already IS this engine's bitmask (LSB-first, 1 = non-null), and
+        nullable integers stay integers (pandas would turn them into float64 + NaN).
+        `pin=True` stages the buffers in pinned host memory (the parquet ingest path,
+        SURVEY.md 8f-1; call site in the reference: bench/examples/dask-nvtabular-criteo-
+        benchmark.py:216 `Dataset(path, engine="parquet", part_size=...)`)."""
+        import pyarrow as pa
+        if isinstance(arr, pa.ChunkedArray):
+            arr = arr.combine_chunks() if arr.num_chunks != 1 else arr.chunk(0)
+        t = arr.type
+        if pa.types.is_dictionary(t):
+            arr = arr.dictionary_decode()
+            t = arr.type
+        device = device or (torch.device("cpu") if pin else default_device())
+
+        def place(np_arr):
+            ten = torch.from_numpy(np_arr)
+            if pin and torch.cuda.is_available():
+                buf = torch.empty(ten.shape, dtype=ten.dtype, pin_memory=True)
+                buf.copy_(ten)
+                return buf
+            return ten.to(device)
+
+        if pa.types.is_string(t) or pa.types.is_large_string(t):
+            return cls.from_strings(arr.to_pylist(), device)
+        if pa.types.is_list(t) or pa.types.is_large_list(t):
+            flat = arr.flatten()                                  # honours slices
+            off = arr.offsets.to_numpy(zero_copy_only=False).astype(np.int64)
+            off = off - off[0]
+            if arr.null_count:                                    # a null row is an empty row
+                lens = np.where(arr.is_valid().to_numpy(zero_copy_only=False), np.diff(off), 0)
+                off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+                flat = pa.concat_arrays([x.values for x in arr if x.is_valid]) if len(arr) else flat
+            leaf = cls.from_arrow(flat, device, pin)
+            leaf.offsets = place(off)
+            return leaf
+        n = len(arr)
+        bufs = arr.buffers()
+        if pa.types.is_boolean(t):
+            vals = arr.fill_null(False).to_numpy(zero_copy_only=False).astype(np.uint8)
+            is_bool = True
+        else:
+            np_dt = np.dtype(t.to_pandas_dtype())
+            if np_dt not in _NP2TORCH:
+                if np.issubdtype(np_dt, np.integer):
+                    arr = arr.cast(pa.int32() if np_dt.itemsize < 4 else pa.int64())
+                elif np.issubdtype(np_dt, np.floating):
+                    arr = arr.cast(pa.float32() if np_dt.itemsize < 4 else pa.float64())
+                else:
+                    raise TypeError(f"unsupported arrow type {t}")
+                bufs = arr.buffers()
+                np_dt = np.dtype(arr.type.to_pandas_dtype())
+            vals = np.frombuffer(bufs[1], dtype=np_dt)[arr.offset: arr.offset + n] if n else np.zeros(0, np_dt)
+            vals = np.array(vals)            # own the memory (the table may be dropped)
+            is_bool = False
+        validity = None
+        if arr.null_count:
+            nbytes = (n + 7) // 8
+            padded = ((nbytes + 31) // 32) * 32
+            out = np.zeros(padded, dtype=np.uint8)
+            if arr.offset % 8 == 0:
+                raw = np.frombuffer(bufs[0], dtype=np.uint8)[arr.offset // 8: arr.offset // 8 + nbytes]
+                out[:nbytes] = raw
+            else:
+                out[:nbytes] = np.packbits(arr.is_valid().to_numpy(zero_copy_only=False), bitorder="little")
+            if n % 8:                            # bits past the last row are zero, like pack_validity
+                out[nbytes - 1] &= (1 << (n % 8)) - 1
+            validity = place(out)
+        col = cls(place(vals), validity)
+        col.is_bool = is_bool
+        return col
+
+    def to_arrow(self):
+        """-> pyarrow Array (host).  Numeric columns reuse the data and bitmask buffers."""
+        import pyarrow as pa
+        if self.dictionary is not None or self.offsets is not None:
+            return pa.Array.from_pandas(self.to_pandas())
+        vals = self.data.detach().cpu().numpy()
+        n = len(vals)
+        if self.is_bool:
+            mask = None
+            if self.validity is not None:
+                mask = ~unpack_validity(self.validity, n).cpu().numpy()
+            return pa.array(vals.astype(bool), mask=mask)
+        vbuf = None
+        nulls = 0
+        if self.validity is not None:
+            bits = self.validity.detach().cpu().numpy()
+            nulls = n - int(unpack_validity(self.validity, n).sum().item())
+            vbuf = pa.py_buffer(bits[: (n + 7) // 8].tobytes()) if nulls else None
+        return pa.Array.from_buffers(pa.from_numpy_dtype(vals.dtype), n, [vbuf, pa.py_buffer(vals)], null_count=nulls)
+
+    @classmethod
     def from_lists(cls, rows, device=None) -> "Column":
         device = device or default_device()
         lens = np.fromiter((0 if r is None else len(r) for r in rows), dtype=np.int64, count=len(rows))
@@ -290,6 +384,15 @@ class DeviceFrame:
     def from_pandas(cls, df: pd.DataFrame, device=None, columns=None) -> "DeviceFrame":
         names = list(columns) if columns is not None else list(df.columns)
         return cls({n: Column.from_pandas(df[n], device) for n in names})
+
+    @classmethod
+    def from_arrow(cls, table, device=None, pin=False, columns=None) -> "DeviceFrame":
+        names = list(columns) if columns is not None else list(table.column_names)
+        return cls({n: Column.from_arrow(table.column(n), device, pin) for n in names})
+
+    def to_arrow(self):
+        import pyarrow as pa
+        return pa.table({k: c.to_arrow() for k, c in self._cols.items()})
 
     @classmethod
     def from_dict(cls, d, device=None) -> "DeviceFrame":

@@ -6,6 +6,7 @@ dask-nvtabular-criteo-benchmark.py:216).  A partition is a DeviceFrame in HBM;
 there is no dask graph — `to_ddf().compute()` simply brings a (lazily
 transformed) dataset back as a pandas frame, as the reference's tests do.
 """
+import os
 from typing import Callable, Iterable, List, Optional, Union
 
 import numpy as np
@@ -74,6 +75,16 @@ class Dataset:
                  part_size=None, schema: Optional[Schema] = None, device=None,
                  _transform: Optional[Callable] = None, base_dataset=None, **kwargs):
         self._device = device
+        # part_size: rows per partition for file sources (int), or None = one per row group;
+        # byte strings ("1GB") are accepted like the reference and mapped through a nominal
+        # 160 B/row (the Criteo-shaped row of SURVEY.md 8d)
+        self._part_rows = None
+        if part_size is not None:
+            if isinstance(part_size, str):
+                from .ops.categorify import _parse_bytes
+                self._part_rows = max(64, int(_parse_bytes(part_size) // 160) // 64 * 64)
+            else:
+                self._part_rows = max(1, int(part_size))
         self.cache_on_device = kwargs.pop("cache_on_device", True)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -95,8 +106,17 @@ class Dataset:
         if isinstance(src, (str, bytes)) or (isinstance(src, (list, tuple)) and src
                                              and all(isinstance(s, str) for s in src)):
             paths = [src] if isinstance(src, (str, bytes)) else list(src)
-            host = [pd.read_parquet(p) if str(p).endswith(".parquet") or not str(p).endswith(".csv")
-                    else pd.read_csv(p) for p in paths]
+            paths = [os.fsdecode(p) for p in paths]
+            expanded = []
+            for p in paths:                     # a directory of part files, like merlin.io.Dataset
+                if os.path.isdir(p):
+                    expanded += sorted(os.path.join(p, f) for f in os.listdir(p)
+                                       if f.endswith(".parquet") or f.endswith(".csv"))
+                else:
+                    expanded.append(p)
+            if all(not p.endswith(".csv") for p in expanded):
+                return self._ingest_parquet(expanded)
+            host = [pd.read_parquet(p) if not p.endswith(".csv") else pd.read_csv(p) for p in expanded]
         elif isinstance(src, pd.DataFrame):
             host = [src]
         elif isinstance(src, DeviceFrame):
@@ -120,6 +140,48 @@ class Dataset:
             chunk = -(-n // k) if n else 0
             host = [df.iloc[i:i + chunk] for i in range(0, n, chunk)] if chunk else [df]
         return [DeviceFrame.from_pandas(h.reset_index(drop=True), self._device) for h in host]
+
+    def _ingest_parquet(self, paths) -> List[DeviceFrame]:
+        """Parquet -> partitions without pandas: one partition per row group (or per
+        `part_size` rows), decoded by pyarrow straight into data + validity-bitmask buffers
+        (nullable int32 stays int32) in pinned host memory; `partitions()` then uploads them
+        one ahead of the consumer.  Replaces merlin.io.Dataset(path, engine="parquet",
+        part_size=...)."""
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+        pin = torch.cuda.is_available()
+        rows_per_part = self._part_rows
+        parts: List[DeviceFrame] = []
+        for p in paths:
+            f = pq.ParquetFile(p)
+            pending, pending_rows = [], 0
+
+            def flush():
+                nonlocal pending, pending_rows
+                if pending:
+                    parts.append(DeviceFrame.from_arrow(pa.concat_tables(pending), self._device, pin))
+                pending, pending_rows = [], 0
+
+            for rg in range(f.num_row_groups):
+                t = f.read_row_group(rg)
+                if rows_per_part is None:
+                    parts.append(DeviceFrame.from_arrow(t, self._device, pin))
+                    continue
+                while len(t):
+                    take = min(len(t), rows_per_part - pending_rows)
+                    pending.append(t.slice(0, take))
+                    pending_rows += take
+                    t = t.slice(take)
+                    if pending_rows == rows_per_part:
+                        flush()
+            flush()
+            if f.num_row_groups == 0:
+                parts.append(DeviceFrame.from_arrow(f.schema_arrow.empty_table(), self._device, pin))
+        if self._npartitions and self._npartitions > 1 and len(parts) == 1 and len(parts[0]):
+            whole, n, k = parts[0], len(parts[0]), self._npartitions
+            chunk = ((-(-n // k)) + 63) // 64 * 64
+            parts = [whole.slice_rows(s0, min(n, s0 + chunk)) for s0 in range(0, n, chunk)]
+        return parts
 
     def partitions(self) -> Iterable[DeviceFrame]:
         """Device-resident partitions, in order.  Partitions that live in (pinned) host
@@ -236,8 +298,8 @@ class Dataset:
         return self
 
     def to_parquet(self, output_path, **kwargs):
-        import os
+        import pyarrow.parquet as pq
         os.makedirs(output_path, exist_ok=True)
         for i, part in enumerate(self.partitions()):
-            part.to_pandas().to_parquet(os.path.join(output_path, f"part_{i}.parquet"))
+            pq.write_table(part.to_arrow(), os.path.join(output_path, f"part_{i}.parquet"))
         return output_path

@@ -212,3 +212,85 @@ def test_bench_clock_sampler_window():
     t = datetime.datetime(2026, 1, 2, 3, 4, 5, 250000)
     assert abs(bench.ClockSampler._epoch(t.strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]) - t.timestamp()) < 1e-3
     assert bench.ClockSampler._epoch("garbage") is None
+
+
+def _frames_equal(a: pd.DataFrame, b: pd.DataFrame):
+    assert list(a.columns) == list(b.columns) and len(a) == len(b)
+    for c in a.columns:
+        x, y = a[c], b[c]
+        if not (pd.api.types.is_numeric_dtype(x.dtype) and pd.api.types.is_numeric_dtype(y.dtype)):
+            for u, v in zip(x.tolist(), y.tolist()):
+                if isinstance(u, (list, np.ndarray)) or isinstance(v, (list, np.ndarray)):
+                    assert list(u) == list(v)
+                else:
+                    assert (u == v) or (pd.isna(u) and pd.isna(v))
+        else:
+            np.testing.assert_array_equal(np.asarray(x, dtype="float64"), np.asarray(y, dtype="float64"))
+
+
+def test_arrow_ingest_keeps_nullable_ints_and_the_bitmask(tmp_path):
+    """Column.from_arrow: data buffer + Arrow validity bitmap map 1:1 onto (data, validity);
+    nullable int32 stays int32 (pandas would make it float64), sliced arrays with a bit offset
+    that is not byte aligned are repacked, bools/strings/lists/dictionaries go through."""
+    import pyarrow as pa
+    from nvtabular_b200.column import Column, DeviceFrame, unpack_validity
+    rng = np.random.default_rng(0)
+    n = 1003
+    vals = rng.integers(-5, 5, n).astype("int32")
+    mask = rng.random(n) < 0.3
+    arr = pa.array(vals, mask=mask)
+    for a in (arr, arr.slice(8, 500), arr.slice(3, 77), pa.chunked_array([arr.slice(0, 10), arr.slice(10)])):
+        col = Column.from_arrow(a, torch.device("cpu"))
+        py = a.to_pylist()
+        assert col.data.dtype == torch.int32 and len(col) == len(py)
+        valid = unpack_validity(col.validity, len(py)).numpy()
+        np.testing.assert_array_equal(valid, np.array([v is not None for v in py]))
+        np.testing.assert_array_equal(col.data.numpy()[valid], np.array([v for v in py if v is not None], dtype="int32"))
+        assert col.validity.numel() % 32 == 0
+        # the round trip back to arrow is exact
+        assert col.to_arrow().to_pylist() == py
+    assert Column.from_arrow(pa.array(vals), torch.device("cpu")).validity is None
+    b = Column.from_arrow(pa.array([True, None, False]), torch.device("cpu"))
+    assert b.is_bool and b.to_arrow().to_pylist() == [True, None, False]
+    s = Column.from_arrow(pa.array(["b", None, "a", "b"]).dictionary_encode(), torch.device("cpu"))
+    sp = s.to_pandas().tolist()
+    assert s.is_string and sp[0] == "b" and pd.isna(sp[1]) and sp[2:] == ["a", "b"]
+    assert s.data.tolist()[0] > s.data.tolist()[2]          # order-preserving codes
+    li = Column.from_arrow(pa.array([[1, 2], [], None, [3]], type=pa.list_(pa.int64())), torch.device("cpu"))
+    assert li.is_list and li.offsets.tolist() == [0, 2, 2, 2, 3] and li.data.tolist() == [1, 2, 3]
+    small = Column.from_arrow(pa.array([1, 2, 3], type=pa.int8()), torch.device("cpu"))
+    assert small.data.dtype == torch.int32
+
+
+def test_parquet_dataset_roundtrip_without_pandas_upcast(tmp_path):
+    """Dataset(path.parquet): one partition per row group (or per part_size rows), nullable
+    int32 columns arrive as int32 + bitmask; to_parquet writes what compute() shows."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    import nvtabular_b200 as nvt
+    rng = np.random.default_rng(1)
+    n = 5000
+    tbl = pa.table({
+        "C1": pa.array(rng.integers(0, 50, n).astype("int32"), mask=rng.random(n) < 0.1),
+        "I1": pa.array(rng.integers(-3, 1000, n).astype("int32"), mask=rng.random(n) < 0.4),
+        "x": pa.array(rng.normal(size=n)),
+        "s": pa.array(rng.choice(["u", "v", "w"], n)),
+    })
+    path = str(tmp_path / "in.parquet")
+    pq.write_table(tbl, path, row_group_size=1200)
+    ds = nvt.Dataset(path, engine="parquet", device=torch.device("cpu"))
+    assert ds.npartitions == 5
+    parts = list(ds.partitions())
+    assert parts[0]["C1"].data.dtype == torch.int32 and parts[0]["C1"].validity is not None
+    assert ds.schema["I1"].dtype == np.dtype("int32")
+    got = ds.to_ddf().compute()
+    _frames_equal(got, tbl.to_pandas())
+    # part_size in rows regroups row groups; a directory of part files is read in name order
+    ds2 = nvt.Dataset(path, part_size=2048, device=torch.device("cpu"))
+    assert [len(p) for p in ds2.partitions()] == [2048, 2048, 904]
+    out_dir = str(tmp_path / "out")
+    ds2.to_parquet(out_dir)
+    back = nvt.Dataset(out_dir, device=torch.device("cpu"))
+    assert back.npartitions == 3
+    _frames_equal(back.to_ddf().compute(), tbl.to_pandas())
+    assert pq.read_table(os.path.join(out_dir, "part_0.parquet")).schema.field("C1").type == pa.int32()
