@@ -4,11 +4,15 @@ The reference without a Dask client computes with scheduler="synchronous"
 (nvtabular/workflow/workflow.py:74; ops/categorify.py:1910-1916) = one core;
 with a LocalCluster it runs one partition per worker and merges partial
 statistics with _mid_level_groupby / _tree_node_moments.  `run_criteo_workflow`
-does exactly that split with a fork-based process pool, so bench.py can time
+does exactly that split with a fork-based process pool (partials and vocabularies
+travel through files, like the reference's on_host spill and unique.<col>.parquet), so bench.py can time
 the reference's CPU path on all host cores (`--impl reference`) or on one
 (`cpu_baseline`)."""
 import multiprocessing as mp
 import os
+import pickle
+import shutil
+import tempfile
 import time
 from typing import List
 
@@ -21,23 +25,45 @@ from .normalize import fill_missing, normalize_transform
 
 _PARTS: List[pd.DataFrame] = []      # inherited by forked workers (no pickling of inputs)
 _STATE = {}
+_VOCAB_CACHE = {}                    # per worker process, like the reference's worker cache
 
 
 def _fit_part(i):
+    """one partition: _top_level_groupby per column (written next to the other partials, as the
+    reference spills them with to_arrow / on_host, categorify.py:1036-1049) + chunk-wise moments"""
     df = _PARTS[i]
-    cats, conts = _STATE["cats"], _STATE["conts"]
-    gbs = {c: _cat.top_level_groupby(df, [c], True)[0] for c in cats}
-    mom = chunkwise_moments(fill_missing(df[conts], conts, 0)) if conts else None
-    return gbs, mom
+    cats, conts, tmp = _STATE["cats"], _STATE["conts"], _STATE["tmp"]
+    for c in cats:
+        _cat.top_level_groupby(df, [c], True)[0].to_pickle(os.path.join(tmp, f"gb.{c}.{i}.pkl"))
+    return chunkwise_moments(fill_missing(df[conts], conts, 0)) if conts else None
 
 
-def _transform_part(i):
+def _merge_col(c):
+    """one column: _mid_level_groupby over every partition's partial + _write_uniques
+    (categorify.py:1054-1337); the vocabulary goes to a file, like unique.<col>.parquet"""
+    tmp, nparts = _STATE["tmp"], _STATE["nparts"]
+    parts = [pd.read_pickle(os.path.join(tmp, f"gb.{c}.{i}.pkl")) for i in range(nparts)]
+    vocab = _cat.write_uniques(_cat.mid_level_groupby(parts, [c]), [c])
+    with open(os.path.join(tmp, f"vocab.{c}.pkl"), "wb") as f:
+        pickle.dump(vocab, f, protocol=pickle.HIGHEST_PROTOCOL)
+    return c
+
+
+def _vocab(c):
+    v = _VOCAB_CACHE.get((_STATE["tmp"], c))
+    if v is None:                      # fetch_table_data's per-worker cache, categorify.py:1627-1643
+        with open(os.path.join(_STATE["tmp"], f"vocab.{c}.pkl"), "rb") as f:
+            v = _VOCAB_CACHE[(_STATE["tmp"], c)] = pickle.load(f)
+    return v
+
+
+def _transform_part(args):
+    i, means, stds = args
     df = _PARTS[i]
     cats, conts = _STATE["cats"], _STATE["conts"]
-    vocabs, means, stds = _STATE["vocabs"], _STATE["means"], _STATE["stds"]
     out = {}
     for c in cats:
-        out[c] = _cat.categorify_encode(df, c, vocabs[c])
+        out[c] = _cat.categorify_encode(df, c, _vocab(c))
     if conts:
         nd = normalize_transform(fill_missing(df[conts], conts, 0), conts, means, stds)
         for c in conts:
@@ -48,43 +74,41 @@ def _transform_part(i):
 
 
 def run_criteo_workflow(df: pd.DataFrame, cats: List[str], conts: List[str], workers: int = 1):
-    """Categorify(cats) + FillMissing + Normalize(conts): fit then transform.
+    """Categorify(cats) + FillMissing + Normalize(conts): fit then transform, as a LocalCluster
+    with `workers` processes would run it: per-partition partials in parallel, the per-column
+    merge + vocabulary write in parallel over columns, the encode in parallel over partitions
+    with the vocabularies read from files by each worker.  ONE pool serves all phases.
     Returns (seconds_fit, seconds_transform, vocabs, means, stds)."""
     global _PARTS
     n = len(df)
     workers = max(1, min(workers, max(1, n // 50_000)))
     chunk = -(-n // workers)
     _PARTS = [df.iloc[i:i + chunk] for i in range(0, n, chunk)]
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    tmp = tempfile.mkdtemp(prefix="nvtb_oracle_", dir=base)
     _STATE.clear()
-    _STATE.update(cats=cats, conts=conts)
+    _STATE.update(cats=cats, conts=conts, tmp=tmp, nparts=len(_PARTS))
     pool = mp.get_context("fork").Pool(workers) if workers > 1 else None
+    pmap = pool.map if pool else (lambda f, xs: [f(x) for x in xs])
     try:
-        t0 = time.perf_counter()
         idx = list(range(len(_PARTS)))
-        res = pool.map(_fit_part, idx) if pool else [_fit_part(i) for i in idx]
-        vocabs = {}
-        for c in cats:
-            gb = _cat.mid_level_groupby([r[0][c] for r in res], [c])
-            vocabs[c] = _cat.write_uniques(gb, [c])
+        t0 = time.perf_counter()
+        moms = pmap(_fit_part, idx)
+        # largest vocabularies first: the phase ends with its slowest column
+        pmap(_merge_col, list(cats))
         means, stds = {}, {}
         if conts:
-            stats = finalize_moments(tree_node_moments([r[1] for r in res]))
+            stats = finalize_moments(tree_node_moments(moms))
             means = {c: float(stats["mean"].loc[c]) for c in conts}
             stds = {c: float(stats["std"].loc[c]) for c in conts}
         t1 = time.perf_counter()
-    finally:
-        if pool:
-            pool.close()
-            pool.join()
-    # transform: a new pool so the fitted state is inherited by fork
-    _STATE.update(vocabs=vocabs, means=means, stds=stds)
-    pool = mp.get_context("fork").Pool(workers) if workers > 1 else None
-    try:
+        _ = pmap(_transform_part, [(i, means, stds) for i in idx])
         t2 = time.perf_counter()
-        _ = pool.map(_transform_part, idx) if pool else [_transform_part(i) for i in idx]
-        t3 = time.perf_counter()
+        vocabs = {c: _vocab(c) for c in cats}
     finally:
         if pool:
             pool.close()
             pool.join()
-    return t1 - t0, t3 - t2, vocabs, means, stds
+        shutil.rmtree(tmp, ignore_errors=True)
+        _VOCAB_CACHE.clear()
+    return t1 - t0, t2 - t1, vocabs, means, stds
