@@ -102,6 +102,18 @@ def main():
         many.append(a)
         local_cols.append(kk.tolist())
     merged = global_merge_many(many, engine=FakeEngine)
+
+    # the same exchange through the round-trip-free owner grouping (counts stay "on device")
+    class AsyncEngine(FakeEngine):
+        @staticmethod
+        def partition_by_owner_async(keys, n_parts, counts_out):
+            perm, cnt = FakeEngine.partition_by_owner(keys, n_parts)
+            counts_out.copy_(torch.tensor(cnt, dtype=torch.int64))
+            return perm
+    merged_async = global_merge_many(many, engine=AsyncEngine)
+    for (k1, s1, n1), (k2, s2, n2) in zip(merged, merged_async):
+        o1, o2 = torch.argsort(k1), torch.argsort(k2)
+        assert torch.equal(k1[o1], k2[o2]) and torch.equal(s1[o1], s2[o2]) and n1 == n2
     res["many"] = []
     for (mk, ms, mns) in merged:
         o = np.argsort(mk.numpy())
