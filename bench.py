@@ -326,6 +326,34 @@ def main():
                     "whole_step_gbs": ALGO_BYTES_PER_ROW * rows / (ms_per_step / 1e3) / 1e9,
                     "whole_step_frac": ALGO_BYTES_PER_ROW * rows / (ms_per_step / 1e3) / 1e9 / peak}
 
+    # ---------------- the same step with the reference's eager artefacts ----------------
+    # `value` runs with NVTB_ARTIFACTS=lazy (config.artifacts); this leg reports what the step
+    # costs when every fit also writes unique.<col>.parquet / meta.<col>.parquet like the
+    # reference does (host-side pandas/pyarrow work, GPU idle meanwhile).  Single GPU only;
+    # a failure here never affects the other numbers.
+    eager = None
+    if world == 1 and not args.eager_artifacts and not args.no_e2e:
+        try:
+            os.environ["NVTB_ARTIFACTS"] = "eager"
+            out = run_step(nvt, wf, frame)
+            del out
+            torch.cuda.synchronize()
+            n_eager = max(1, min(args.steps, 3))
+            ev0.record()
+            for _ in range(n_eager):
+                out = run_step(nvt, wf, frame)
+                del out
+            ev1.record()
+            torch.cuda.synchronize()
+            e_ms = ev0.elapsed_time(ev1) / n_eager
+            eager = {"ms_per_step": e_ms, "value": total_rows / (e_ms / 1e3), "unit": "rows/s", "steps": n_eager,
+                     "what": "library default: every meta.<col>.parquet and the unique.<col>.parquet of every "
+                             "vocabulary up to 2^20 keys written during fit"}
+        except Exception as exc:          # noqa: BLE001 - reported, not fatal
+            eager = {"error": repr(exc)[:200]}
+        finally:
+            os.environ["NVTB_ARTIFACTS"] = "lazy"
+
     # ---------------- end to end from pinned host buffers ---------------------------
     e2e = None
     if not args.no_e2e:
@@ -394,7 +422,8 @@ def main():
                    "artifacts": "eager" if args.eager_artifacts else
                                 "unique./meta. parquet files deferred until read (NVTB_ARTIFACTS=lazy)",
                    "parallelism": f"row-sharded x{world}, key-hash owner merge over NCCL" if world > 1 else "single GPU"},
-        "roofline": roofline, "kernels": kernels, "e2e": e2e, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "kernels": kernels, "e2e": e2e, "eager_artifacts": eager,
+        "cpu_baseline": cpu_baseline,
         "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line))
