@@ -122,9 +122,17 @@ def build_workflow(nvt, out_path, int32_outputs=False):
     return nvt.Workflow(cats + conts + ["label"])
 
 
-def run_step(nvt, wf, frame):
-    """one pass of the hot path over the resident table: fit, then transform"""
-    ds = nvt.Dataset(frame)
+def device_partitions(frame, nparts):
+    """the resident table cut into `nparts` row partitions (views, 64-row aligned)"""
+    rows = len(frame)
+    chunk = ((rows + nparts - 1) // nparts + 63) // 64 * 64
+    return [frame.slice_rows(s, min(rows, s + chunk)) for s in range(0, rows, chunk)]
+
+
+def run_step(nvt, wf, parts):
+    """one pass of the hot path over the resident table: fit (accumulated over the
+    partitions), then transform partition by partition (outputs of one partition live at a time)"""
+    ds = nvt.Dataset(list(parts))
     wf.fit(ds)
     out = None
     for part in wf.transform(ds).partitions():
@@ -186,7 +194,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=1 << 26, help="rows resident per GPU")
+    ap.add_argument("--rows", type=int, default=250_000_000, help="rows resident per GPU (SURVEY 8d C2: 2.5e8)")
+    ap.add_argument("--parts", type=int, default=4, help="device-resident partitions the table is cut into")
+    ap.add_argument("--profile-rows", type=int, default=4_370_000_000,
+                    help="row count the categorical cardinalities are scaled to (4.37e9 = the full Criteo-1TB profile)")
     ap.add_argument("--e2e-rows", type=int, default=0, help="rows per e2e step (default: same table)")
     ap.add_argument("--e2e-parts", type=int, default=8, help="host partitions per e2e step")
     ap.add_argument("--cpu-rows", type=int, default=1 << 20, help="rows of the bounded CPU sample")
@@ -239,7 +250,8 @@ def main():
 
     rows = args.rows
     total_rows = rows * world
-    frame = criteo_frame(rows, total_rows=total_rows, device=dev, rank=rank)
+    frame = criteo_frame(rows, total_rows=args.profile_rows, device=dev, rank=rank)
+    frame = device_partitions(frame, args.parts)
     out_dir = f"/tmp/nvtb_bench_rank{rank}"
     wf = build_workflow(nvt, out_dir, args.int32_outputs)
 

@@ -190,6 +190,24 @@ int nvtb_hashagg_export(nvtb_hashagg_t* h, int64_t* keys_out,
                         int64_t* sizes_out, double* vals_out,
                         double* null_vals_host, void* stream);
 
+/* 0 = resident hash table, 1 = sorted accumulator.  int32 key columns whose expected number
+ * of distinct keys exceeds NVTB_RUNS_MIN_KEYS (default 2^23: the table would leave the L2)
+ * are accumulated as a key-ordered array of packed (key, count) pairs: every batch is
+ * radix-sorted, run-length encoded and merged in (csrc/sortagg.cuh) — the streaming
+ * replacement of the per-partition groupby + concat/groupby tree of reference
+ * nvtabular/ops/categorify.py:955-1137 for the C20/C1/C22/C10 class of Criteo columns. */
+int nvtb_hashagg_mode(nvtb_hashagg_t* h, int* mode_host);
+
+/* Stable LSD radix sort of device arrays by bits [lo_bit, hi_bit) of every element
+ * (csrc/radix.cuh; ascending, or descending on that bit field).  data/tmp: n elements
+ * each, 16-byte aligned; the result ends in data (*result_in_tmp_host = 0) or tmp (= 1).
+ * This is the ordering primitive behind sort_values in reference
+ * nvtabular/ops/categorify.py:1300,1316. */
+int nvtb_radix_sort_u32(uint32_t* data, uint32_t* tmp, int64_t n, int lo_bit, int hi_bit,
+                        int descending, int* result_in_tmp_host, void* stream);
+int nvtb_radix_sort_u64(uint64_t* data, uint64_t* tmp, int64_t n, int lo_bit, int hi_bit,
+                        int descending, int* result_in_tmp_host, void* stream);
+
 /* owner = mix(key) % n_parts for the key-hash sharding across GPUs
  * (the reference's split_out shuffle_group,
  * categorify.py:1036-1049).  perm_out receives a permutation that groups
@@ -246,6 +264,14 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys,
                      int64_t freq_threshold, int64_t max_size,
                      int64_t num_buckets, int key_bits, int64_t size_bound,
                      void* stream);
+/* the same straight from a group-by handle (single GPU: _write_uniques reads the result of
+ * _bottom_level_groupby without leaving the device, categorify.py:1149-1337).  A handle
+ * holding a sorted accumulator is already in key order, so the ordering is one stable
+ * radix sort on the size bits in use; null_size comes from the handle. */
+int nvtb_vocab_build_from_hashagg(nvtb_vocab_t** out, nvtb_hashagg_t* h,
+                                  int64_t freq_threshold, int64_t max_size,
+                                  int64_t num_buckets, int key_bits, int64_t size_bound,
+                                  void* stream);
 int nvtb_vocab_from_arrays(nvtb_vocab_t** out, const int64_t* keys,
                            const int64_t* sizes, int64_t n, void* stream);
 int nvtb_vocab_destroy(nvtb_vocab_t* v);

@@ -50,13 +50,13 @@ struct Rows8 { int32_t v[8]; unsigned m; unsigned lv; };
 
 __device__ __forceinline__ void load_rows8(const int32_t* __restrict__ keys,
                                            const uint8_t* __restrict__ mask, int64_t i,
-                                           int64_t end, Rows8& r) {
-  if (i + 8 <= end) {
+                                           int64_t end, Rows8& r, bool aligned = true) {
+  if (i + 8 <= end && aligned) {
     ld_rows8<int32_t>(keys + i, r.v);
     r.lv = 0xFFu;
     r.m = valid8(mask, i);
   } else if (i < end) {
-    r.lv = (1u << (unsigned)(end - i)) - 1u;
+    r.lv = (end - i >= 8) ? 0xFFu : ((1u << (unsigned)(end - i)) - 1u);
     r.m = valid8(mask, i) & r.lv;
 #pragma unroll
     for (int k = 0; k < 8; ++k) r.v[k] = (i + k < end) ? keys[i + k] : 0;
@@ -254,10 +254,27 @@ fold_i32_kernel(const int32_t* __restrict__ keys, const uint8_t* __restrict__ ma
 // ---------------------------------------------------------------------------------------
 // hash partition of the valid keys of a column
 // ---------------------------------------------------------------------------------------
+// What a key becomes in the partition buffer, and which partition it goes to:
+//   PartHashTop  h = fold_hash(key), partition = top lg bits of h   (shared-memory fold)
+//   PartKeyLow   u = key ^ 2^31 (unsigned order == signed order), partition = LOW lg bits
+//                of u: the first, order-free pass of the LSD radix sort of sortagg.cuh
+struct PartHashTop {
+  int lg;
+  __device__ __forceinline__ uint32_t xform(uint32_t k) const { return fold_hash(k); }
+  __device__ __forceinline__ uint32_t bin(uint32_t v) const { return v >> (32 - lg); }
+};
+struct PartKeyLow {
+  int lg;
+  __device__ __forceinline__ uint32_t xform(uint32_t k) const { return k ^ 0x80000000u; }
+  __device__ __forceinline__ uint32_t bin(uint32_t v) const { return v & ((1u << lg) - 1u); }
+};
+
 // (1) partition sizes; the nulls are counted here and dropped by the scatter
+template <typename Pol>
 __global__ void __launch_bounds__(kPartThreads)
 part_hist_kernel(const int32_t* __restrict__ keys, const uint8_t* __restrict__ mask, int64_t n,
-                 int lg, uint32_t* __restrict__ total, Counters* ctr) {
+                 Pol pol, uint32_t* __restrict__ total, Counters* ctr, int aligned) {
+  const int lg = pol.lg;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw);
   const int P = 1 << lg;
@@ -271,13 +288,13 @@ part_hist_kernel(const int32_t* __restrict__ keys, const uint8_t* __restrict__ m
     Rows8 r[kPartGroups];
 #pragma unroll
     for (int g = 0; g < kPartGroups; ++g)
-      load_rows8(keys, mask, tile * kPartTile + ((int64_t)g * kPartThreads + threadIdx.x) * 8, n, r[g]);
+      load_rows8(keys, mask, tile * kPartTile + ((int64_t)g * kPartThreads + threadIdx.x) * 8, n, r[g], aligned != 0);
 #pragma unroll
     for (int g = 0; g < kPartGroups; ++g) {
       n_null += __popc(r[g].lv & ~r[g].m);
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        if ((r[g].m >> k) & 1u) atomicAdd(&cnt[fold_hash((uint32_t)r[g].v[k]) >> (32 - lg)], 1u);
+        if ((r[g].m >> k) & 1u) atomicAdd(&cnt[pol.bin(pol.xform((uint32_t)r[g].v[k]))], 1u);
     }
   }
   if (n_null) atomicAdd(&s_null, n_null);
@@ -326,19 +343,21 @@ __device__ __forceinline__ void block_excl_scan(const uint32_t* vals, uint32_t* 
   __syncthreads();
 }
 
-// (2) partition starts (multiples of 8 rows = 32 bytes, so the fold kernel can use 256-bit
-// loads), write cursors = starts
-__global__ void __launch_bounds__(kPartThreads)
+// (2) partition starts (rounded up to multiples of `round` rows: 8 rows = 32 bytes for the
+// fold kernel's 256-bit loads, 1 = dense for the radix sort), write cursors = starts;
+// n_total (may be NULL) receives the end of the last partition
+static __global__ void __launch_bounds__(kPartThreads)
 part_scan_kernel(const uint32_t* __restrict__ total, int lg, uint32_t* __restrict__ starts,
-                 uint32_t* __restrict__ cursor) {
+                 uint32_t* __restrict__ cursor, uint32_t round, uint32_t* __restrict__ n_total) {
   __shared__ uint32_t v[kMaxParts];
   __shared__ uint32_t o[kMaxParts];
   __shared__ uint32_t ws[kPartThreads / 32];
   const int P = 1 << lg;
   for (int d = threadIdx.x; d < P; d += kPartThreads) v[d] = total[d];
   __syncthreads();
-  block_excl_scan<kPartThreads>(v, o, P, 8u, ws);
+  block_excl_scan<kPartThreads>(v, o, P, round, ws);
   for (int d = threadIdx.x; d < P; d += kPartThreads) { starts[d] = o[d]; cursor[d] = o[d]; }
+  if (n_total != nullptr && threadIdx.x == 0) *n_total = o[P - 1] + (v[P - 1] + round - 1) / round * round;
 }
 
 // (3) scatter (the buffer receives h = fold_hash(key), which the fold kernel consumes as
@@ -346,9 +365,11 @@ part_scan_kernel(const uint32_t* __restrict__ total, int lg, uint32_t* __restric
 // tile's run in every partition with ONE global atomic per non-empty (tile, partition),
 // bin the keys in shared memory, then copy the staged tile out so that consecutive lanes
 // write consecutive words of a run.  Order inside a partition is irrelevant (counting).
+template <typename Pol>
 __global__ void __launch_bounds__(kPartThreads, 2)
 part_scatter_kernel(const int32_t* __restrict__ keys, const uint8_t* __restrict__ mask, int64_t n,
-                    int lg, uint32_t* __restrict__ cursor, int32_t* __restrict__ out) {
+                    Pol pol, uint32_t* __restrict__ cursor, int32_t* __restrict__ out, int aligned) {
+  const int lg = pol.lg;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* stage = reinterpret_cast<int32_t*>(smem_raw);                 // [kPartTile]
   uint32_t* cnt = reinterpret_cast<uint32_t*>(stage + kPartTile);        // [P] counts, then running cursors
@@ -363,13 +384,13 @@ part_scatter_kernel(const int32_t* __restrict__ keys, const uint8_t* __restrict_
     Rows8 r[kPartGroups];
 #pragma unroll
     for (int g = 0; g < kPartGroups; ++g)
-      load_rows8(keys, mask, tile * kPartTile + ((int64_t)g * kPartThreads + threadIdx.x) * 8, n, r[g]);
+      load_rows8(keys, mask, tile * kPartTile + ((int64_t)g * kPartThreads + threadIdx.x) * 8, n, r[g], aligned != 0);
 #pragma unroll
     for (int g = 0; g < kPartGroups; ++g)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        r[g].v[k] = (int32_t)fold_hash((uint32_t)r[g].v[k]);      // the buffer holds hashes
-        if ((r[g].m >> k) & 1u) atomicAdd(&cnt[(uint32_t)r[g].v[k] >> (32 - lg)], 1u);
+        r[g].v[k] = (int32_t)pol.xform((uint32_t)r[g].v[k]);      // the buffer holds hashes / biased keys
+        if ((r[g].m >> k) & 1u) atomicAdd(&cnt[pol.bin((uint32_t)r[g].v[k])], 1u);
       }
     __syncthreads();
     // staged offsets (exclusive scan of the counts, in place via `delta` as scratch)
@@ -388,14 +409,14 @@ part_scatter_kernel(const int32_t* __restrict__ keys, const uint8_t* __restrict_
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         if ((r[g].m >> k) & 1u) {
-          const uint32_t p = atomicAdd(&cnt[(uint32_t)r[g].v[k] >> (32 - lg)], 1u);
+          const uint32_t p = atomicAdd(&cnt[pol.bin((uint32_t)r[g].v[k])], 1u);
           stage[p] = r[g].v[k];
         }
     __syncthreads();
     const uint32_t total = s_total;
     for (uint32_t j = threadIdx.x; j < total; j += kPartThreads) {
       const int32_t hv = stage[j];
-      out[delta[(uint32_t)hv >> (32 - lg)] + j] = hv;
+      out[delta[pol.bin((uint32_t)hv)] + j] = hv;
     }
     __syncthreads();
   }

@@ -86,7 +86,7 @@ struct Counters {
   unsigned long long n_unique;   // distinct keys in the table
   unsigned long long size[2];    // special groups: [0] null key, [1] INT64_MIN key
   unsigned long long ovf_count;  // pairs refused into the arena by the pending launch
-  long long reserved;
+  unsigned long long max_count;  // sorted accumulator (sortagg.cuh): largest group size seen
 };
 
 struct Arena {
@@ -115,6 +115,12 @@ struct nvtb_hashagg {
   int64_t hint;
   int n_agg;
   bool mailbox_valid;        // mailbox == device counters (no launch / host edit since the readback)
+  // sorted accumulator (sortagg.cuh), mode == 1: acc[acc_cur] holds ctr->n_unique packed pairs
+  int mode;                  // 0 = hash table, 1 = sorted runs
+  uint64_t* acc[2];
+  int64_t acc_cap[2];
+  int acc_cur;
+  uint32_t* d_n;             // device uint32[4]: [1] valid keys of the batch, [2] distinct keys of the batch
 };
 
 namespace nvtb {
@@ -282,7 +288,7 @@ __global__ void arm_launch_kernel(Counters* ctr) {
 
 __global__ void special_init_kernel(Counters* ctr, double* special_vals, int n_agg) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    ctr->n_unique = 0; ctr->size[0] = 0; ctr->size[1] = 0; ctr->ovf_count = 0; ctr->reserved = 0;
+    ctr->n_unique = 0; ctr->size[0] = 0; ctr->size[1] = 0; ctr->ovf_count = 0; ctr->max_count = 0;
     for (int g = 0; g < 2; ++g)
       for (int j = 0; j < n_agg; ++j) {
         double* v = special_vals + (g * n_agg + j) * 4;
@@ -295,6 +301,10 @@ __global__ void special_init_kernel(Counters* ctr, double* special_vals, int n_a
 
 }  // namespace nvtb
 #include "fold_i32.cuh"
+namespace nvtb {
+constexpr int kExportPerThread = 4;
+}
+#include "sortagg.cuh"
 namespace nvtb {
 
 // ---------------------------------------------------------------------------
@@ -695,7 +705,6 @@ rehash_kernel(Table old_t, Table new_t) {
 // reserves its output range with ONE atomic: a per-warp atomicAdd on the single cursor
 // (500 k same-address atomics for a 16 M-slot table) serialised at ~1 ns each and cost
 // ~20x the time the scan itself needs.
-constexpr int kExportPerThread = 4;
 __global__ void __launch_bounds__(kThreads)
 export_kernel(Table t, int64_t* __restrict__ keys_out,
               int64_t* __restrict__ sizes_out, double* __restrict__ vals_out,
@@ -1086,8 +1095,8 @@ static int post(nvtb_hashagg* h, cudaStream_t st) {
   return NVTB_OK;
 }
 
-// size the table for `rows` more rows: load <= 0.5 for the ESTIMATED distinct count
-static int prepare(nvtb_hashagg* h, int64_t rows, cudaStream_t st) {
+// distinct keys expected in the table after `rows` more rows (-> h->predicted)
+static void predict(nvtb_hashagg* h, int64_t rows) {
   double predicted;
   if (h->hint > 0) {
     predicted = (double)std::max<int64_t>(h->hint, h->u_known);
@@ -1099,7 +1108,12 @@ static int prepare(nvtb_hashagg* h, int64_t rows, cudaStream_t st) {
   }
   predicted = std::min(predicted, (double)h->u_known + (double)rows);
   h->predicted = predicted;
-  const int64_t want = next_pow2((int64_t)(2.5 * predicted) + 1);
+}
+
+// size the table for `rows` more rows: load <= 0.5 for the ESTIMATED distinct count
+static int prepare(nvtb_hashagg* h, int64_t rows, cudaStream_t st) {
+  predict(h, rows);
+  const int64_t want = next_pow2((int64_t)(2.5 * h->predicted) + 1);
   return grow_to(h, want, st);
 }
 
@@ -1119,7 +1133,7 @@ static int launch_fold_i32(nvtb_hashagg* h, const int32_t* kp, const uint8_t* mp
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kDirectSmem));
     NVTB_CUDA_OK(cudaFuncSetAttribute(fold_i32_kernel<kFoldThreadsParts, 2, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kPartsSmem));
-    NVTB_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel,
+    NVTB_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<PartHashTop>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmemMax));
     attrs = true;
   }
@@ -1167,13 +1181,13 @@ static int launch_fold_i32(nvtb_hashagg* h, const int32_t* kp, const uint8_t* mp
   }
   NVTB_CUDA_OK(cudaMemsetAsync(meta, 0, sizeof(uint32_t) * P, st));
   const int64_t tiles = (m + kPartTile - 1) / kPartTile;
-  part_hist_kernel<<<(int)std::min<int64_t>(tiles, 3 * sms), kPartThreads, 4 * P, st>>>(
-      kp, mp, m, lg, meta, h->ctr);
+  part_hist_kernel<PartHashTop><<<(int)std::min<int64_t>(tiles, 3 * sms), kPartThreads, 4 * P, st>>>(
+      kp, mp, m, PartHashTop{lg}, meta, h->ctr, 1);
   NVTB_LAUNCH_OK();
-  part_scan_kernel<<<1, kPartThreads, 0, st>>>(meta, lg, meta + P, meta + 2 * P);
+  part_scan_kernel<<<1, kPartThreads, 0, st>>>(meta, lg, meta + P, meta + 2 * P, 8u, nullptr);
   NVTB_LAUNCH_OK();
-  part_scatter_kernel<<<(int)std::min<int64_t>(tiles, 2 * sms), kPartThreads, kPartTile * 4 + 2 * 4 * P, st>>>(
-      kp, mp, m, lg, meta + 2 * P, buf);
+  part_scatter_kernel<PartHashTop><<<(int)std::min<int64_t>(tiles, 2 * sms), kPartThreads, kPartTile * 4 + 2 * 4 * P, st>>>(
+      kp, mp, m, PartHashTop{lg}, meta + 2 * P, buf, 1);
   NVTB_LAUNCH_OK();
   fold_i32_kernel<kFoldThreadsParts, 2, true><<<std::min(P, 2 * sms), kFoldThreadsParts, kPartsSmem, st>>>(
       buf, nullptr, m + 8 * (int64_t)P, meta + P, meta + 2 * P, P, 0, lg, kFoldBucketsParts, 1,
@@ -1186,6 +1200,193 @@ static int launch_fold_i32(nvtb_hashagg* h, const int32_t* kp, const uint8_t* mp
     g_part.last = st;
   }
   return NVTB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// sorted accumulator (sortagg.cuh): host side
+// ---------------------------------------------------------------------------------------
+// expected distinct keys above which an int32 column leaves the hash table for the sorted
+// accumulator: the table (2.5 slots x 8 B per key) then no longer stays in the 126 MB L2
+static int64_t runs_min_keys() {
+  const char* e = getenv("NVTB_RUNS_MIN_KEYS");      // read every time: tests flip it
+  int64_t v = e ? atoll(e) : ((int64_t)8 << 20);
+  return v < 1 ? 1 : v;
+}
+
+// ONE grow-only device scratch for the sort pipeline, shared by every handle of the process
+// (one process per GPU); uses on different streams are ordered by an event, like g_part
+struct SortScratch { void* ptr; size_t bytes; cudaEvent_t ev; cudaStream_t last; bool used; };
+static SortScratch g_sort = {nullptr, 0, nullptr, nullptr, false};
+
+struct SortCarve {
+  unsigned int* rx_zero;     // 256 B kept at zero (radix "done" counter)
+  void* rx;                  // radix scratch (starts at rx_zero)
+  uint32_t* part_meta;       // total[P] | starts[P] | cursor[P]
+  uint32_t* keys_a;
+  uint32_t* keys_b;
+  uint64_t* rle;             // [m + 1]
+  uint32_t* tile_heads;      // [ceil(m / kRleTile)]
+  uint2* splits;             // [MT + 1]
+  uint32_t* tile_out;        // [MT]
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int sort_scratch_acquire(int64_t m, int64_t n_pairs_sort, int64_t mt, cudaStream_t st, SortCarve* c) {
+  const int P = 1 << kSortLowBits;
+  const size_t rx_bytes = align_up(std::max(rx_scratch_bytes<uint32_t>(m, kRxMaxStableBits - 1),
+                                            rx_scratch_bytes<uint64_t>(n_pairs_sort, kRxMaxStableBits - 1)), 256);
+  const size_t meta_bytes = align_up(sizeof(uint32_t) * 3 * P, 256);
+  const size_t keys_bytes = align_up(sizeof(uint32_t) * (size_t)(m + 64), 256);
+  const size_t rle_bytes = align_up(sizeof(uint64_t) * (size_t)(m + 2), 256);
+  const size_t heads_bytes = align_up(sizeof(uint32_t) * (size_t)((m + kRleTile - 1) / kRleTile + 1), 256);
+  const size_t splits_bytes = align_up(sizeof(uint2) * (size_t)(mt + 2), 256);
+  const size_t out_bytes = align_up(sizeof(uint32_t) * (size_t)(mt + 2), 256);
+  const size_t need = rx_bytes + meta_bytes + 2 * keys_bytes + rle_bytes + heads_bytes + splits_bytes + out_bytes;
+  std::lock_guard<std::recursive_mutex> lk(g_arena_mu);
+  if (g_sort.bytes < need) {
+    NVTB_CUDA_OK(cudaDeviceSynchronize());
+    if (g_sort.ptr) cudaFree(g_sort.ptr);
+    g_sort.ptr = nullptr; g_sort.bytes = 0;
+    const size_t want = need + need / 8;
+    NVTB_CUDA_OK(cudaMalloc(&g_sort.ptr, want));
+    g_sort.bytes = want;
+    NVTB_CUDA_OK(cudaMemsetAsync(g_sort.ptr, 0, 256, st));
+    g_sort.used = false;
+  }
+  if (g_sort.ev == nullptr) NVTB_CUDA_OK(cudaEventCreateWithFlags(&g_sort.ev, cudaEventDisableTiming));
+  if (g_sort.used && g_sort.last != st) NVTB_CUDA_OK(cudaStreamWaitEvent(st, g_sort.ev, 0));
+  char* p = reinterpret_cast<char*>(g_sort.ptr);
+  c->rx_zero = reinterpret_cast<unsigned int*>(p);
+  c->rx = p;                                         p += rx_bytes;
+  c->part_meta = reinterpret_cast<uint32_t*>(p);     p += meta_bytes;
+  c->keys_a = reinterpret_cast<uint32_t*>(p);        p += keys_bytes;
+  c->keys_b = reinterpret_cast<uint32_t*>(p);        p += keys_bytes;
+  c->rle = reinterpret_cast<uint64_t*>(p);           p += rle_bytes;
+  c->tile_heads = reinterpret_cast<uint32_t*>(p);    p += heads_bytes;
+  c->splits = reinterpret_cast<uint2*>(p);           p += splits_bytes;
+  c->tile_out = reinterpret_cast<uint32_t*>(p);
+  return NVTB_OK;
+}
+
+static int sort_scratch_release(cudaStream_t st) {
+  std::lock_guard<std::recursive_mutex> lk(g_arena_mu);
+  NVTB_CUDA_OK(cudaEventRecord(g_sort.ev, st));
+  g_sort.used = true;
+  g_sort.last = st;
+  return NVTB_OK;
+}
+
+// make sure acc[which] can hold `pairs` packed pairs (contents are NOT preserved)
+static int acc_reserve(nvtb_hashagg* h, int which, int64_t pairs, cudaStream_t st) {
+  if (h->acc_cap[which] >= pairs) return NVTB_OK;
+  if (h->acc[which]) NVTB_CUDA_OK(cudaFreeAsync(h->acc[which], st));
+  h->acc[which] = nullptr; h->acc_cap[which] = 0;
+  const int64_t want = pairs + pairs / 8 + 1024;
+  NVTB_CUDA_OK(cudaMallocAsync(&h->acc[which], sizeof(uint64_t) * (size_t)want, st));
+  h->acc_cap[which] = want;
+  return NVTB_OK;
+}
+
+// hash table -> sorted accumulator (the handle must be settled and its table narrow).
+// One-off: export the u_known (key, count) pairs packed and sort them by key.
+static int table_to_runs(nvtb_hashagg* h, cudaStream_t st) {
+  const int64_t nu = h->u_known;
+  if (h->d_n == nullptr) {
+    NVTB_CUDA_OK(cudaMalloc(&h->d_n, sizeof(uint32_t) * 4));
+    NVTB_CUDA_OK(cudaMemsetAsync(h->d_n, 0, sizeof(uint32_t) * 4, st));
+  }
+  h->acc_cur = 0;
+  if (nu > 0) {
+    int rc = acc_reserve(h, 0, nu, st);
+    if (rc) return rc;
+    rc = acc_reserve(h, 1, nu, st);
+    if (rc) return rc;
+    SortCarve c;
+    rc = sort_scratch_acquire(64, nu, 1, st, &c);
+    if (rc) return rc;
+    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(c.part_meta);
+    NVTB_CUDA_OK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
+    table_to_pairs_kernel<<<plain_grid(h->t.capacity / kExportPerThread), kThreads, 0, st>>>(
+        h->t, h->acc[0], cursor, &h->ctr->max_count);
+    NVTB_LAUNCH_OK();
+    int in_b = 0;
+    rc = rx_sort_bits<uint64_t>(h->acc[0], h->acc[1], nullptr, nu, 32, 64, false, c.rx, st, &in_b);
+    if (rc) return rc;
+    h->acc_cur = in_b;
+    rc = sort_scratch_release(st);
+    if (rc) return rc;
+  }
+  // the table itself is no longer used: keep a minimal one so that the handle stays uniform
+  int rc = table_free(&h->t, st);
+  if (rc) return rc;
+  rc = table_alloc(&h->t, kMinCapacity, 0, true, st);
+  if (rc) return rc;
+  h->mode = 1;
+  return NVTB_OK;
+}
+
+// fold one batch of int32 keys into the sorted accumulator (handle settled: u_known exact)
+static int launch_runs_insert(nvtb_hashagg* h, const int32_t* kp, const uint8_t* mp, int64_t m, cudaStream_t st) {
+  static bool attrs = false;
+  constexpr int kScatterSmem = kPartTile * 4 + 2 * 4 * (1 << kSortLowBits);
+  if (!attrs) {
+    NVTB_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<PartKeyLow>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
+    NVTB_CUDA_OK(cudaFuncSetAttribute(merge_write_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
+    attrs = true;
+  }
+  const int64_t ua = h->u_known;
+  const int other = h->acc_cur ^ 1;
+  int rc = acc_reserve(h, other, ua + m, st);
+  if (rc) return rc;
+  const int64_t mt = (ua + m + kMergeTile - 1) / kMergeTile;
+  SortCarve c;
+  rc = sort_scratch_acquire(m, 64, mt, st, &c);
+  if (rc) return rc;
+  const int sms = sm_count();
+  const int P = 1 << kSortLowBits;
+  const int aligned = is_aligned32(kp) ? 1 : 0;
+  uint32_t* n_valid = h->d_n + 1;
+  uint32_t* n_batch = h->d_n + 2;
+  // (1) LSD radix sort of the valid keys (as key ^ 2^31)
+  NVTB_CUDA_OK(cudaMemsetAsync(c.part_meta, 0, sizeof(uint32_t) * P, st));
+  const int64_t tiles = (m + kPartTile - 1) / kPartTile;
+  part_hist_kernel<PartKeyLow><<<(int)std::min<int64_t>(tiles, 3 * sms), kPartThreads, 4 * P, st>>>(
+      kp, mp, m, PartKeyLow{kSortLowBits}, c.part_meta, h->ctr, aligned);
+  NVTB_LAUNCH_OK();
+  part_scan_kernel<<<1, kPartThreads, 0, st>>>(c.part_meta, kSortLowBits, c.part_meta + P, c.part_meta + 2 * P, 1u, n_valid);
+  NVTB_LAUNCH_OK();
+  part_scatter_kernel<PartKeyLow><<<(int)std::min<int64_t>(tiles, 2 * sms), kPartThreads, kScatterSmem, st>>>(
+      kp, mp, m, PartKeyLow{kSortLowBits}, c.part_meta + 2 * P, reinterpret_cast<int32_t*>(c.keys_a), aligned);
+  NVTB_LAUNCH_OK();
+  int in_b = 0;
+  rc = rx_sort_bits<uint32_t>(c.keys_a, c.keys_b, n_valid, m, kSortLowBits, 32, false, c.rx, st, &in_b);
+  if (rc) return rc;
+  const uint32_t* sorted = in_b ? c.keys_b : c.keys_a;
+  // (2) run heads
+  const int rt = (int)((m + kRleTile - 1) / kRleTile);
+  rle_count_kernel<<<rt, kRunThreads, 0, st>>>(sorted, n_valid, m, c.tile_heads);
+  NVTB_LAUNCH_OK();
+  scan_tiles_kernel<<<1, kRunThreads, 0, st>>>(c.tile_heads, rt, n_batch, nullptr);
+  NVTB_LAUNCH_OK();
+  rle_write_kernel<<<rt, kRunThreads, 0, st>>>(sorted, n_valid, m, c.tile_heads, n_batch, c.rle);
+  NVTB_LAUNCH_OK();
+  // (3) merge with the accumulator
+  const uint64_t* A = h->acc[h->acc_cur];
+  merge_split_kernel<<<(int)((mt + 1 + 255) / 256), 256, 0, st>>>(A, (uint32_t)ua, c.rle, n_batch, (int)mt, c.splits);
+  NVTB_LAUNCH_OK();
+  merge_count_kernel<<<(int)mt, kRunThreads, 0, st>>>(A, c.rle, c.splits, c.tile_out);
+  NVTB_LAUNCH_OK();
+  scan_tiles_kernel<<<1, kRunThreads, 0, st>>>(c.tile_out, (int)mt, nullptr, &h->ctr->n_unique);
+  NVTB_LAUNCH_OK();
+  merge_write_kernel<<<(int)mt, kRunThreads, sizeof(MergeSmem), st>>>(A, c.rle, c.splits, c.tile_out, h->acc[other],
+                                                                     &h->ctr->max_count);
+  NVTB_LAUNCH_OK();
+  h->acc_cur = other;
+  return sort_scratch_release(st);
 }
 
 template <typename KeyT>
@@ -1218,6 +1419,21 @@ static int launch_insert(nvtb_hashagg* h, const KeyT* kp, const uint8_t* mp, con
   NVTB_LAUNCH_OK();
   h->rows_total += m;
   return post(h, st);
+}
+
+// view of a handle for nvtb_vocab_build_from_hashagg (vocab.cu): synchronises on the handle's
+// pending launch.  *pairs == nullptr when the handle is a hash table (the caller exports).
+int hashagg_sorted_view(nvtb_hashagg* h, const uint64_t** pairs, int64_t* n_unique, int64_t* null_size,
+                        uint64_t* max_count, int* is_i32_table, cudaStream_t st) {
+  int64_t nu = 0, ns = 0;
+  int rc = nvtb_hashagg_size(h, &nu, &ns, (void*)st);
+  if (rc) return rc;
+  *n_unique = nu;
+  *null_size = ns;
+  *max_count = (uint64_t)h->mailbox->max_count;
+  *pairs = h->mode == 1 ? h->acc[h->acc_cur] : nullptr;
+  *is_i32_table = (h->mode == 0 && h->t.narrow) ? 1 : 0;
+  return NVTB_OK;
 }
 
 }  // namespace nvtb
@@ -1257,8 +1473,10 @@ int nvtb_hashagg_reset(nvtb_hashagg_t* h, void* stream) {
   // the table keeps its capacity (and the estimate its value): a second fit over
   // similar data needs no growth and no sampling pass
   h->hint = std::max<int64_t>(h->hint, h->u_known);
-  table_init_kernel<<<plain_grid(h->t.capacity), kThreads, 0, st>>>(h->t);
-  NVTB_LAUNCH_OK();
+  if (h->mode == 0) {      // a sorted accumulator is emptied by zeroing its counters below
+    table_init_kernel<<<plain_grid(h->t.capacity), kThreads, 0, st>>>(h->t);
+    NVTB_LAUNCH_OK();
+  }
   special_init_kernel<<<1, 32, 0, st>>>(h->ctr, h->special_vals, h->n_agg);
   NVTB_LAUNCH_OK();
   h->u_known = 0;
@@ -1277,6 +1495,9 @@ int nvtb_hashagg_destroy(nvtb_hashagg_t* h) {
   if (h->special_vals) cudaFree(h->special_vals);
   if (h->mailbox) cudaFreeHost(h->mailbox);
   if (h->ev) cudaEventDestroy(h->ev);
+  if (h->acc[0]) cudaFree(h->acc[0]);
+  if (h->acc[1]) cudaFree(h->acc[1]);
+  if (h->d_n) cudaFree(h->d_n);
   delete h;
   return NVTB_OK;
 }
@@ -1304,7 +1525,9 @@ int nvtb_hashagg_insert(nvtb_hashagg_t* h, const nvtb_col_t* key,
     if (rc) return rc;
     const bool can_narrow = h->n_agg == 0 && key->dtype == NVTB_I32 &&
                             h->rows_total + n < (int64_t)0xFFFFFFF0ll;
-    if (h->rows_total == 0 && h->u_known == 0 && can_narrow && !h->t.narrow) {
+    if (h->mode == 1) {
+      // sorted accumulator: nothing to switch
+    } else if (h->rows_total == 0 && h->u_known == 0 && can_narrow && !h->t.narrow) {
       // empty table: switch to the 8-byte layout in place
       const int64_t cap = h->t.capacity;
       rc = table_free(&h->t, st);
@@ -1322,12 +1545,34 @@ int nvtb_hashagg_insert(nvtb_hashagg_t* h, const nvtb_col_t* key,
     int rc = settle(h);
     if (rc) return rc;
     int64_t m = n - off;
-    const bool blind = (h->hint == 0 && h->k_est == 0);
+    const bool blind = (h->mode == 0 && h->hint == 0 && h->k_est == 0);
     if (blind && m > 4 * kSampleRows) m = kSampleRows;
-    rc = prepare(h, m, st);
-    if (rc) return rc;
     const void* kp = (const char*)key->data + off * ksz;
     const uint8_t* mp = key->validity ? key->validity + (off >> 3) : nullptr;  // off % 8 == 0
+    if (h->mode == 0) {
+      // a column whose table would leave the L2 moves to the sorted accumulator (sortagg.cuh)
+      predict(h, m);
+      const bool eligible = h->n_agg == 0 && key->dtype == NVTB_I32 && h->t.narrow &&
+                            h->rows_total + n < (int64_t)0xFFFFFFF0ll && m < (int64_t)0xFFFF0000ll;
+      if (eligible && h->predicted > (double)runs_min_keys()) {
+        rc = table_to_runs(h, st);
+        if (rc) return rc;
+      }
+    }
+    if (h->mode == 1) {
+      NVTB_REQUIRE(h->n_agg == 0 && key->dtype == NVTB_I32, "a sorted accumulator takes int32 keys without payload");
+      NVTB_REQUIRE(h->rows_total + m < (int64_t)0xFFFFFFF0ll, "more than 2^32 rows in one int32 accumulator");
+      int64_t mm = m < (int64_t)0xFFFF0000ll ? m : (int64_t)0x80000000ll;
+      rc = launch_runs_insert(h, (const int32_t*)kp, mp, mm, st);
+      if (rc) return rc;
+      h->rows_total += mm;
+      rc = post(h, st);
+      if (rc) return rc;
+      off += mm;
+      continue;
+    }
+    rc = prepare(h, m, st);
+    if (rc) return rc;
     AggCols a2 = ac;
     for (int j = 0; j < h->n_agg; ++j) {
       a2.data[j] = (const char*)ac.data[j] + off * dtype_size(ac.dtype[j]);
@@ -1351,6 +1596,10 @@ int nvtb_hashagg_merge(nvtb_hashagg_t* h, const int64_t* keys,
   cudaStream_t st = (cudaStream_t)stream;
   int rc = settle(h);
   if (rc) return rc;
+  if (h->mode == 1) {
+    set_error("nvtb_hashagg_merge: the handle holds a sorted accumulator (raw int32 rows only)");
+    return NVTB_ESTATE;
+  }
   // pre-aggregated rows: distinct keys within the batch => every row may be new; sizes are
   // arbitrary int64 => wide layout
   rc = grow_to(h, next_pow2((int64_t)(2.5 * (double)(h->u_known + n)) + 1), st, /*force_wide=*/true);
@@ -1433,6 +1682,11 @@ int nvtb_hashagg_export(nvtb_hashagg_t* h, int64_t* keys_out, int64_t* sizes_out
   if (nu == 0) return NVTB_OK;
   NVTB_REQUIRE(keys_out != nullptr, "keys_out is NULL");
   NVTB_REQUIRE(h->n_agg == 0 || vals_out != nullptr, "vals_out is NULL");
+  if (h->mode == 1) {      // sorted accumulator: unpack (the rows come out in key order)
+    runs_unpack_kernel<<<plain_grid(nu), kThreads, 0, st>>>(h->acc[h->acc_cur], nu, keys_out, sizes_out);
+    NVTB_LAUNCH_OK();
+    return NVTB_OK;
+  }
   unsigned long long* cursor = nullptr;
   NVTB_CUDA_OK(cudaMallocAsync(&cursor, sizeof(unsigned long long), st));
   NVTB_CUDA_OK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
@@ -1449,6 +1703,51 @@ int nvtb_hashagg_export(nvtb_hashagg_t* h, int64_t* keys_out, int64_t* sizes_out
                                    sizeof(double) * 4 * h->n_agg, cudaMemcpyHostToDevice, st));
     NVTB_CUDA_OK(cudaStreamSynchronize(st));  // host temporaries above
   }
+  return NVTB_OK;
+}
+
+// Stable LSD radix sort of bits [lo_bit, hi_bit) (radix.cuh), exposed for tests and for
+// callers that order their own device arrays.  The result ends in `data` or in `tmp`
+// (*result_in_tmp_host).
+static int radix_sort_entry(void* data, void* tmp, int64_t n, int elem_bytes, int lo_bit, int hi_bit,
+                            int descending, int* result_in_tmp_host, void* stream) {
+  NVTB_REQUIRE(n >= 0 && result_in_tmp_host != nullptr, "bad n / NULL result flag");
+  NVTB_REQUIRE(lo_bit >= 0 && hi_bit <= 8 * elem_bytes && lo_bit <= hi_bit, "bad bit range");
+  *result_in_tmp_host = 0;
+  if (n == 0 || lo_bit == hi_bit) return NVTB_OK;
+  NVTB_REQUIRE(data != nullptr && tmp != nullptr, "NULL data/tmp");
+  NVTB_REQUIRE((reinterpret_cast<uintptr_t>(data) & 15u) == 0 && (reinterpret_cast<uintptr_t>(tmp) & 15u) == 0,
+               "data/tmp must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  void* scratch = nullptr;
+  const size_t bytes = elem_bytes == 4 ? rx_scratch_bytes<uint32_t>(n, kRxMaxStableBits - 1)
+                                       : rx_scratch_bytes<uint64_t>(n, kRxMaxStableBits - 1);
+  NVTB_CUDA_OK(cudaMallocAsync(&scratch, bytes, st));
+  NVTB_CUDA_OK(cudaMemsetAsync(scratch, 0, 256, st));
+  int rc;
+  if (elem_bytes == 4)
+    rc = rx_sort_bits<uint32_t>((uint32_t*)data, (uint32_t*)tmp, nullptr, n, lo_bit, hi_bit, descending != 0, scratch, st,
+                                result_in_tmp_host);
+  else
+    rc = rx_sort_bits<uint64_t>((uint64_t*)data, (uint64_t*)tmp, nullptr, n, lo_bit, hi_bit, descending != 0, scratch, st,
+                                result_in_tmp_host);
+  NVTB_CUDA_OK(cudaFreeAsync(scratch, st));
+  return rc;
+}
+
+int nvtb_radix_sort_u32(uint32_t* data, uint32_t* tmp, int64_t n, int lo_bit, int hi_bit, int descending,
+                        int* result_in_tmp_host, void* stream) {
+  return radix_sort_entry(data, tmp, n, 4, lo_bit, hi_bit, descending, result_in_tmp_host, stream);
+}
+
+int nvtb_radix_sort_u64(uint64_t* data, uint64_t* tmp, int64_t n, int lo_bit, int hi_bit, int descending,
+                        int* result_in_tmp_host, void* stream) {
+  return radix_sort_entry(data, tmp, n, 8, lo_bit, hi_bit, descending, result_in_tmp_host, stream);
+}
+
+int nvtb_hashagg_mode(nvtb_hashagg_t* h, int* mode_host) {
+  NVTB_REQUIRE(h != nullptr && mode_host != nullptr, "NULL argument");
+  *mode_host = h->mode;
   return NVTB_OK;
 }
 

@@ -21,6 +21,14 @@
 #include <vector>
 
 #include "common.cuh"
+#include "radix.cuh"
+
+struct nvtb_hashagg;
+namespace nvtb {
+// hashagg.cu: view of a handle's sorted accumulator (pairs == nullptr: hash table)
+int hashagg_sorted_view(nvtb_hashagg* h, const uint64_t** pairs, int64_t* n_unique, int64_t* null_size,
+                        uint64_t* max_count, int* is_i32_table, cudaStream_t st);
+}
 
 namespace nvtb {
 
@@ -459,6 +467,50 @@ gather_stats_kernel(const KeyT* __restrict__ keys, const uint8_t* __restrict__ m
   }
 }
 
+// ---- vocabularies from packed, key-ordered pairs (sorted accumulator of hashagg.cu) ------
+__device__ __forceinline__ long long packed_key(uint64_t w) { return (long long)(int32_t)((uint32_t)(w >> 32) ^ 0x80000000u); }
+
+__global__ void __launch_bounds__(kThreads)
+packed_unpack_kernel(const uint64_t* __restrict__ p, int64_t n, int64_t* __restrict__ keys, int64_t* __restrict__ sizes) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t w = p[i];
+    if (keys) keys[i] = packed_key(w);
+    if (sizes) sizes[i] = (int64_t)(uint32_t)w;
+  }
+}
+
+// number of leading pairs with size >= threshold in a size-descending packed array
+__global__ void __launch_bounds__(kThreads)
+packed_count_ge_kernel(const uint64_t* __restrict__ p, int64_t n, int64_t threshold, long long* out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t c = (int64_t)(uint32_t)p[i];
+    if (c >= threshold && (i == n - 1 || (int64_t)(uint32_t)p[i + 1] < threshold)) *out = i + 1;
+  }
+}
+
+struct VocabScalars;
+__global__ void packed_scalars_kernel(const uint64_t* __restrict__ p, int64_t n, int64_t n_keep, VocabScalars* sc);
+
+// narrow lookup (4-way sector buckets of ((pos + 1) << 32) | key) from the kept pairs; keys are distinct
+__global__ void __launch_bounds__(kThreads)
+lookup_build_packed_kernel(const uint64_t* __restrict__ p, int64_t n, unsigned long long* __restrict__ slots,
+                           int64_t capacity) {
+  const int64_t bmask = (capacity >> 2) - 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t key = (uint32_t)(p[i] >> 32) ^ 0x80000000u;
+    const unsigned long long want = ((unsigned long long)(unsigned)(i + 1) << 32) | key;
+    int64_t b = (int64_t)((uint64_t)table_mix32(key) & (uint64_t)bmask);
+    bool placed = false;
+    while (!placed) {
+      for (int j = 0; j < 4 && !placed; ++j) placed = (atomicCAS(slots + 4 * b + j, 0ull, want) == 0ull);
+      b = (b + 1) & bmask;
+    }
+  }
+}
+
 static int64_t pow2_at_least(int64_t v) {
   int64_t p = 16;
   while (p < v) p <<= 1;
@@ -526,6 +578,26 @@ vocab_scalars_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict
     if (all) atomicAdd(reinterpret_cast<unsigned long long*>(&sc->sum_all), (unsigned long long)all);
   }
   if (bad) sc->fit_i32 = 0;
+}
+
+__global__ void __launch_bounds__(kThreads)
+packed_scalars_kernel(const uint64_t* __restrict__ p, int64_t n, int64_t n_keep, VocabScalars* sc) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  long long kept = 0, all = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long sz = (long long)(uint32_t)p[i];
+    all += sz;
+    if (i < n_keep) kept += sz;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kept += __shfl_down_sync(0xffffffffu, kept, o);
+    all += __shfl_down_sync(0xffffffffu, all, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (kept) atomicAdd(reinterpret_cast<unsigned long long*>(&sc->sum_kept), (unsigned long long)kept);
+    if (all) atomicAdd(reinterpret_cast<unsigned long long*>(&sc->sum_all), (unsigned long long)all);
+  }
 }
 
 // build either layout; which one is decided by a DEVICE flag so no host sync is needed
@@ -739,6 +811,10 @@ struct nvtb_vocab {
   nvtb::Lookup t;
   int64_t* keys;   // device [n_kept], label order
   int64_t* sizes;  // device [n_kept] or nullptr
+  // vocabularies built from a sorted accumulator keep the ordered PACKED pairs
+  // ((key ^ 2^31) << 32 | size) instead of two int64 arrays; keys[] is then only
+  // materialised for the shared-memory encode (<= kEncSmemMaxKeys keys)
+  uint64_t* packed;
   nvtb_vocab_info_t info;
   // nvtb_vocab_build enqueues everything and returns; the scalars it needs on the host
   // (n_kept, meta sums, table layout) arrive in a pinned mailbox and are read by the first
@@ -980,6 +1056,132 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* siz
   return NVTB_OK;
 }
 
+
+// Vocabulary straight from a group-by handle (single GPU: no int64 export round trip).
+//   sorted accumulator  the pairs are already in key order, so (size desc, key asc) is ONE
+//                       stable radix sort on the size bits that are in use (max size from
+//                       the handle's counters: 8-10 bits = one pass for the high-cardinality
+//                       columns this path exists for), then cut, meta sums and the lookup
+//                       build read the packed pairs directly
+//   hash table          exported into temporaries and handed to nvtb_vocab_build
+int nvtb_vocab_build_from_hashagg(nvtb_vocab_t** out, nvtb_hashagg_t* h, int64_t freq_threshold,
+                                  int64_t max_size, int64_t num_buckets, int key_bits,
+                                  int64_t size_bound, void* stream) {
+  NVTB_REQUIRE(out != nullptr && h != nullptr, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t* pairs = nullptr;
+  int64_t n = 0, null_size = 0;
+  uint64_t maxc = 0;
+  int is_i32 = 0;
+  int rc = hashagg_sorted_view(h, &pairs, &n, &null_size, &maxc, &is_i32, st);
+  if (rc) return rc;
+  if (pairs == nullptr || n == 0 || n >= (int64_t)0x7FFFFFF0) {
+    int64_t *k = nullptr, *s = nullptr;
+    if (n > 0) {
+      NVTB_CUDA_OK(cudaMallocAsync(&k, sizeof(int64_t) * n, st));
+      NVTB_CUDA_OK(cudaMallocAsync(&s, sizeof(int64_t) * n, st));
+      rc = nvtb_hashagg_export(h, k, s, nullptr, nullptr, stream);
+      if (rc) return rc;
+    }
+    rc = nvtb_vocab_build(out, k, s, n, null_size, freq_threshold, max_size, num_buckets,
+                          (key_bits > 0 || is_i32) ? 32 : 0, size_bound, stream);
+    if (k) cudaFreeAsync(k, st);
+    if (s) cudaFreeAsync(s, st);
+    return rc;
+  }
+  ensure_pool_configured();
+  NVTB_REQUIRE(!(freq_threshold > 0 && max_size > 0), "cannot use freq_threshold together with max_size");
+  const int64_t oov_count = num_buckets > 0 ? num_buckets : 1;
+  NVTB_REQUIRE(!(max_size > 0 && max_size < oov_count + 2),
+               "`max_size` can never be less than the maximum of `num_buckets + 2` and `3`");
+  nvtb_vocab* v = new (std::nothrow) nvtb_vocab();
+  NVTB_REQUIRE(v != nullptr, "host allocation failed");
+  memset(v, 0, sizeof(*v));
+  v->info.n_total = n;
+  v->info.null_size = null_size;
+  // (1) stable sort on the size, descending, over the bits in use
+  int bits = 0;
+  while (bits < 32 && (maxc >> bits) != 0) ++bits;
+  uint64_t *p0 = nullptr, *p1 = nullptr;
+  NVTB_CUDA_OK(cudaMallocAsync(&p0, sizeof(uint64_t) * n, st));
+  uint64_t* sorted = p0;
+  if (bits <= 1) {            // every size is 1 (or there is one size only): key order is the order
+    NVTB_CUDA_OK(cudaMemcpyAsync(p0, pairs, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, st));
+  } else {
+    constexpr int kPref = 10;
+    const int passes = (bits + kPref - 1) / kPref;
+    const int per = (bits + passes - 1) / passes;
+    void* scratch = nullptr;
+    const size_t sbytes = rx_scratch_bytes<uint64_t>(n, kRxMaxStableBits - 1);
+    NVTB_CUDA_OK(cudaMallocAsync(&scratch, sbytes, st));
+    NVTB_CUDA_OK(cudaMemsetAsync(scratch, 0, 256, st));
+    const RxScratch sc = rx_scratch_carve(scratch, rx_tiles<uint64_t>(n), kRxMaxStableBits - 1);
+    if (passes > 1) NVTB_CUDA_OK(cudaMallocAsync(&p1, sizeof(uint64_t) * n, st));
+    const uint64_t* src = pairs;
+    uint64_t* dst = p0;
+    int bit = 0;
+    for (int p = 0; p < passes; ++p) {
+      const int w = (bits - bit < per) ? bits - bit : per;
+      BitsDigit fn{bit, (1u << w) - 1u, (1u << w) - 1u};
+      rc = rx_pass<uint64_t, BitsDigit>(src, dst, nullptr, n, fn, w, sc, st);
+      if (rc) return rc;
+      sorted = dst;
+      src = dst;
+      dst = (dst == p0) ? p1 : p0;
+      bit += w;
+    }
+    NVTB_CUDA_OK(cudaFreeAsync(scratch, st));
+    if (sorted == p0) { if (p1) NVTB_CUDA_OK(cudaFreeAsync(p1, st)); }
+    else NVTB_CUDA_OK(cudaFreeAsync(p0, st));
+  }
+  v->packed = sorted;
+  // (2) cut + meta sums
+  int64_t n_keep = n;
+  VocabScalars* d_sc = nullptr;
+  NVTB_CUDA_OK(cudaMallocAsync(&d_sc, sizeof(VocabScalars), st));
+  const VocabScalars init = {n, 0, 0, 1, -1};
+  NVTB_CUDA_OK(cudaMemcpyAsync(d_sc, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+  const int g = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
+  if (freq_threshold > 0) {
+    NVTB_CUDA_OK(cudaMemsetAsync(&d_sc->n_keep, 0, sizeof(long long), st));
+    packed_count_ge_kernel<<<g, kThreads, 0, st>>>(sorted, n, freq_threshold, &d_sc->n_keep);
+    NVTB_LAUNCH_OK();
+    VocabScalars hs;
+    NVTB_CUDA_OK(cudaMemcpyAsync(&hs, d_sc, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    NVTB_CUDA_OK(cudaStreamSynchronize(st));
+    n_keep = hs.n_keep;
+  } else if (max_size > 0) {
+    n_keep = std::min<int64_t>(n, max_size - (oov_count + 2));
+    NVTB_CUDA_OK(cudaMemcpyAsync(&d_sc->n_keep, &n_keep, sizeof(long long), cudaMemcpyHostToDevice, st));
+    NVTB_CUDA_OK(cudaStreamSynchronize(st));      // n_keep is a host temporary
+  }
+  packed_scalars_kernel<<<g, kThreads, 0, st>>>(sorted, n, n_keep, d_sc);
+  NVTB_LAUNCH_OK();
+  v->info.n_kept = n_keep;
+  // (3) narrow lookup of the kept keys
+  v->t.capacity = pow2_at_least(2 * n_keep);
+  v->t.min_key_pos = -1;
+  v->t.narrow = 1;
+  NVTB_CUDA_OK(cudaMallocAsync(&v->t.slots, sizeof(int64_t) * v->t.capacity, st));
+  NVTB_CUDA_OK(cudaMemsetAsync(v->t.slots, 0, sizeof(int64_t) * v->t.capacity, st));
+  if (n_keep > 0) {
+    const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>((n_keep + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
+    lookup_build_packed_kernel<<<g1, kThreads, 0, st>>>(sorted, n_keep, reinterpret_cast<unsigned long long*>(v->t.slots),
+                                                        v->t.capacity);
+    NVTB_LAUNCH_OK();
+    if (n_keep <= kEncSmemMaxKeys) {        // the shared-memory encode reads int64 keys
+      NVTB_CUDA_OK(cudaMallocAsync(&v->keys, sizeof(int64_t) * n_keep, st));
+      packed_unpack_kernel<<<g1, kThreads, 0, st>>>(sorted, n_keep, v->keys, nullptr);
+      NVTB_LAUNCH_OK();
+    }
+  }
+  v->d_sc = d_sc;
+  rc = vocab_post(v, st);
+  if (rc) { nvtb_vocab_destroy(v); return rc; }
+  *out = v;
+  return NVTB_OK;
+}
+
 int nvtb_vocab_from_arrays(nvtb_vocab_t** out, const int64_t* keys, const int64_t* sizes,
                            int64_t n, void* stream) {
   NVTB_REQUIRE(out != nullptr && n >= 0, "out NULL or n < 0");
@@ -1013,6 +1215,7 @@ int nvtb_vocab_destroy(nvtb_vocab_t* v) {
   if (v->t.slots) cudaFreeAsync(v->t.slots, 0);
   if (v->keys) cudaFreeAsync(v->keys, 0);
   if (v->sizes) cudaFreeAsync(v->sizes, 0);
+  if (v->packed) cudaFreeAsync(v->packed, 0);
   delete v;
   return NVTB_OK;
 }
@@ -1030,6 +1233,12 @@ int nvtb_vocab_export(const nvtb_vocab_t* v, int64_t* keys_out, int64_t* sizes_o
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = v->info.n_kept;
   if (n == 0) return NVTB_OK;
+  if (v->packed != nullptr) {
+    const int g = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
+    packed_unpack_kernel<<<g, kThreads, 0, st>>>(v->packed, n, keys_out, sizes_out);
+    NVTB_LAUNCH_OK();
+    return NVTB_OK;
+  }
   if (keys_out)
     NVTB_CUDA_OK(cudaMemcpyAsync(keys_out, v->keys, sizeof(int64_t) * n, cudaMemcpyDeviceToDevice, st));
   if (sizes_out) {

@@ -97,7 +97,13 @@ class Dataset:
         if isinstance(data, Dataset):
             self._source = data._source
             self._parts = data._parts
-            self._transform = _transform or data._transform
+            # a lazily transformed Dataset handed to another Workflow: CHAIN the transforms
+            # (wf2.transform(wf1.transform(ds)) runs wf2 on wf1's output, like the reference)
+            prev = data._transform
+            if prev is not None and _transform is not None:
+                self._transform = lambda part, _f=prev, _g=_transform: _g(_f(part))
+            else:
+                self._transform = _transform or prev
         self._schema = schema
 
     # --------------------------------------------------------------- ingestion
@@ -220,6 +226,8 @@ class Dataset:
                     c.data.record_stream(main)
                     if c.validity is not None:
                         c.validity.record_stream(main)
+                    if c.offsets is not None:
+                        c.offsets.record_stream(main)
                 if self.cache_on_device:
                     parts[i] = d
                 p = d
@@ -257,7 +265,10 @@ class Dataset:
                         hv = torch.empty(c.validity.shape, dtype=torch.uint8, pin_memory=True)
                         hv.copy_(c.validity, non_blocking=True)
                         c.validity.record_stream(out_stream)
-                    cols[name] = Column(hb, hv, c.offsets.cpu() if c.offsets is not None else None)
+                    hc = Column(hb, hv, c.offsets.cpu() if c.offsets is not None else None,
+                                c.dictionary, None, c.is_bool)
+                    hc.prehashed = c.prehashed
+                    cols[name] = hc
                     self.d2h_bytes += hb.numel() * hb.element_size()
             res.append(DeviceFrame(cols))
         out_stream.synchronize()

@@ -28,6 +28,18 @@ def world():
     return 1, 0
 
 
+def all_gather_object(obj):
+    """[obj of rank 0, obj of rank 1, ...] on every rank (host metadata only: fit modes,
+    string dictionaries — never row data)."""
+    import torch.distributed as dist
+    w, _ = world()
+    if w == 1:
+        return [obj]
+    out = [None] * w
+    dist.all_gather_object(out, obj)
+    return out
+
+
 def exchange_by_owner(keys, sizes, vals, perm, counts):
     """all-to-all of rows already grouped by owner (perm/counts from
     nvtb_partition_by_owner).  Returns the rows this rank owns."""

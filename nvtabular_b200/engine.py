@@ -257,6 +257,13 @@ class HashAgg:
         _lib.check(self.lib.nvtb_hashagg_reset(self.h, _lib.stream_ptr()))
         _count(2)
 
+    @property
+    def mode(self) -> int:
+        """0 = resident hash table, 1 = sorted accumulator (csrc/sortagg.cuh)"""
+        m = c_int(0)
+        _lib.check(self.lib.nvtb_hashagg_mode(self.h, byref(m)))
+        return m.value
+
     def insert(self, key: Column, agg_cols: Sequence[Column] = ()):
         n = key.data.numel()
         assert len(agg_cols) == self.n_agg
@@ -379,6 +386,21 @@ class Vocab:
         return cls(h, lib, n_total=keys.numel())
 
     @classmethod
+    def build_from_agg(cls, agg: "HashAgg", freq_threshold=0, max_size=0, num_buckets=0, key_bits=0,
+                       size_bound=0):
+        """vocabulary straight from a group-by handle (single GPU): no int64 export round
+        trip; a sorted accumulator only needs one stable sort on the size bits."""
+        _lib.require_cuda()
+        lib = _lib.load()
+        h = c_void_p()
+        with _timed("vocab_build", 0.0):
+            _lib.check(lib.nvtb_vocab_build_from_hashagg(byref(h), agg.h, int(freq_threshold or 0), int(max_size or 0),
+                                                         int(num_buckets or 0), int(key_bits), int(size_bound),
+                                                         _lib.stream_ptr()))
+        _count(8)
+        return cls(h, lib)
+
+    @classmethod
     def from_arrays(cls, keys: torch.Tensor, sizes: Optional[torch.Tensor] = None):
         _lib.require_cuda()
         lib = _lib.load()
@@ -413,6 +435,24 @@ class Vocab:
                 _ptr(out), code, _lib.stream_ptr()))
         _count()
         return out
+
+
+def radix_sort(data: torch.Tensor, lo_bit: int = 0, hi_bit: Optional[int] = None, descending=False) -> torch.Tensor:
+    """stable LSD radix sort of an int32/int64 tensor by bits [lo_bit, hi_bit) of its
+    elements viewed as unsigned (nvtb_radix_sort_u32/u64); returns the sorted tensor"""
+    _lib.require_cuda()
+    lib = _lib.load()
+    assert data.dtype in (torch.int32, torch.int64) and data.is_contiguous()
+    bits = 8 * data.element_size()
+    hi_bit = bits if hi_bit is None else hi_bit
+    a = data.clone()
+    b = torch.empty_like(a)
+    flag = c_int(0)
+    fn = lib.nvtb_radix_sort_u32 if bits == 32 else lib.nvtb_radix_sort_u64
+    _lib.check(fn(_ptr(a), _ptr(b), a.numel(), int(lo_bit), int(hi_bit), 1 if descending else 0, byref(flag),
+                  _lib.stream_ptr()))
+    _count(3)
+    return b if flag.value else a
 
 
 class GroupStats:

@@ -286,12 +286,27 @@ class Categorify(StatOperator):
             return {}
         it = iter(ddf)
         first = next(it, None)
-        if first is None:
+        # Every rank must issue the SAME sequence of collectives, so the path is agreed on
+        # first: a rank whose shard is empty (or whose first partition is not streamable while
+        # the others' are) follows the majority instead of picking a path from local data.
+        from ..dist import all_gather_object, world
+        mode = "empty" if first is None else ("stream" if self._streamable(first, groups) else "general")
+        wide = {}
+        if first is not None and mode == "stream":
+            wide = {storage: any(_leaf(first[n]).data.dtype == torch.int64 for n in names)
+                    for storage, names in groups}
+        if world()[0] > 1:
+            seen = all_gather_object((mode, wide))
+            live = [m for m, _ in seen if m != "empty"]
+            mode = "empty" if not live else ("stream" if all(m == "stream" for m in live) else "general")
+            wide = {storage: any(w.get(storage, False) for _, w in seen) for storage, _ in groups}
+        if mode == "empty":
             return {storage: self._fit_group(storage, names, []) for storage, names in groups}
-        if self._streamable(first, groups):
+        if mode == "stream":
             # numeric keys: ONE streaming pass — partition i is folded into the tables while
             # partition i+1 is still being uploaded (Dataset.partitions prefetches one ahead)
-            state = {storage: self._open_group(storage, names, first) for storage, names in groups}
+            state = {storage: self._open_group(storage, names, first, wide.get(storage, False))
+                     for storage, names in groups}
             part = first
             while part is not None:
                 for storage, names in groups:
@@ -299,12 +314,16 @@ class Categorify(StatOperator):
                     for n in names:
                         self._insert(storage, agg, space.keys_for(part[n]))
                 part = next(it, None)
+            if world()[0] == 1:
+                # single GPU: every vocabulary is built straight from its handle
+                return {storage: self._close_group(storage, [storage], state[storage][0], state[storage][1], "direct")
+                        for storage, names in groups}
             from ..dist import global_merge_many
             merged = global_merge_many([state[storage][1] for storage, _ in groups], owner_pool=self._owner_pool)
             self._rows_bound_global = _global_rows(max(self._rows_seen.values(), default=0))
             return {storage: self._close_group(storage, [storage], state[storage][0], state[storage][1], m)
                     for (storage, names), m in zip(groups, merged)}
-        parts = [first] + list(it)   # strings / general combos need a dictionary pre-pass
+        parts = ([first] if first is not None else []) + list(it)   # strings / general combos: dictionary pre-pass
         fitted = {}
         for storage, names in groups:
             fitted[storage] = self._fit_group(storage, names, parts)
@@ -338,20 +357,31 @@ class Categorify(StatOperator):
             return self._rows_seen.get(storage, 0)
         return self._rows_bound_global            # 0 = unknown
 
-    def _open_group(self, storage, names, df):
-        space = KeySpace.for_columns([_leaf(df[n]) for n in names])
+    def _open_group(self, storage, names, df, wide=False):
+        """streaming path: numeric keys only; `wide` (agreed across ranks) = some rank holds int64"""
+        if df is None:
+            space = KeySpace("int", None, np.dtype("int64") if wide else np.dtype("int32"))
+        else:
+            space = KeySpace.for_columns([_leaf(df[n]) for n in names], sync=False)
+            if space.kind == "int" and wide:
+                space.np_dtype = np.dtype("int64")
         return space, self._get_agg(storage)
 
     def _close_group(self, storage, key_names, space, agg, merged=None) -> FittedVocab:
-        keys, sizes, null_size = merged if merged is not None else _global_unique_merge(agg)
+        direct = isinstance(merged, str)
+        if not direct:
+            keys, sizes, null_size = merged if merged is not None else _global_unique_merge(agg)
         ft = _resolve(self.freq_threshold, storage, 0) or 0
         ms = _resolve(self.max_size, storage, 0) or 0
         nb = self._nb(storage)
         try:
             key_bits = 32 if isinstance(space, KeySpace) and (space.kind == "str" or (
                 space.kind == "int" and space.np_dtype == np.dtype("int32"))) else 0
-            vocab = engine.Vocab.build(keys, sizes, null_size, ft, ms, nb or 0, key_bits,
-                                       self._size_bound(storage))
+            if direct:
+                vocab = engine.Vocab.build_from_agg(agg, ft, ms, nb or 0, key_bits, self._size_bound(storage))
+            else:
+                vocab = engine.Vocab.build(keys, sizes, null_size, ft, ms, nb or 0, key_bits,
+                                           self._size_bound(storage))
         except Exception as e:
             if "max_size" in str(e):     # categorify.py:1206-1211
                 raise ValueError(
@@ -374,11 +404,11 @@ class Categorify(StatOperator):
             comp_parts = [[_leaf(df[n]) for n in names] for df in parts]
             if any(c.is_list for df in parts for c in (df[n] for n in names)):
                 raise ValueError("Can't categorical encode multiple list columns")
-            space = ComboKeySpace.fit(comp_parts) if parts else ComboKeySpace([KeySpace("int")] * len(names))
+            space = ComboKeySpace.fit(comp_parts, ncomp=len(names))
             key_names = names
         else:
             cols_all = [df[n] for df in parts for n in names]
-            space = KeySpace.for_columns([_leaf(c) for c in cols_all]) if cols_all else KeySpace("int", None, np.dtype("int64"))
+            space = KeySpace.for_columns([_leaf(c) for c in cols_all])
             key_names = [storage]
         agg = self._get_agg(storage)
         for df in parts:
@@ -387,7 +417,9 @@ class Categorify(StatOperator):
             else:
                 for n in names:          # joint encoding: every column feeds the SAME table
                     self._insert(storage, agg, space.keys_for(df[n]))
-        return self._close_group(storage, key_names, space, agg)
+        merged = _global_unique_merge(agg)
+        self._rows_bound_global = _global_rows(self._rows_seen.get(storage, 0))
+        return self._close_group(storage, key_names, space, agg, merged)
 
     def fit_finalize(self, categories):
         base = os.path.join(self.out_path, "categories")

@@ -57,20 +57,48 @@ class KeySpace:
         self._lut_cache = {}
 
     @classmethod
-    def for_columns(cls, cols: Sequence[Column]) -> "KeySpace":
-        """Union key space of several columns (joint encoding / partitions)."""
-        first = cols[0]
-        if first.is_string:
-            if not all(c.is_string for c in cols):
-                raise TypeError("cannot jointly encode string and non-string columns")
-            parts = [c.dictionary for c in cols if len(c.dictionary)]
-            uni = np.array(sorted(set(np.concatenate(parts).tolist())), dtype=object) if parts \
-                else np.array([], dtype=object)
-            return cls("str", uni)
-        if first.data.dtype in (torch.float32, torch.float64):
-            return cls("float", None, first.np_dtype)
-        widest = np.dtype("int64") if any(c.data.dtype == torch.int64 for c in cols) else np.dtype("int32")
-        return cls("int", None, widest)
+    def for_columns(cls, cols: Sequence[Column], sync: bool = True) -> "KeySpace":
+        """Union key space of several columns (joint encoding / partitions).
+
+        Under torch.distributed (one process per GPU) the key space must be IDENTICAL on
+        every rank before keys are exchanged by owner: string dictionaries are rank-local,
+        so with `sync` the ranks all-gather their distinct strings and build the same union
+        dictionary (and agree on the numeric width; a rank with no rows adopts the others').
+        This is a collective: every rank must make the same sequence of synced calls.
+        `sync=False` is for callers that have already agreed on a numeric dtype."""
+        kind, np_dtype, uni = None, None, None
+        if cols:
+            first = cols[0]
+            if first.is_string:
+                if not all(c.is_string for c in cols):
+                    raise TypeError("cannot jointly encode string and non-string columns")
+                parts = [c.dictionary for c in cols if len(c.dictionary)]
+                uni = np.array(sorted(set(np.concatenate(parts).tolist())), dtype=object) if parts \
+                    else np.array([], dtype=object)
+                kind = "str"
+            elif first.data.dtype in (torch.float32, torch.float64):
+                kind, np_dtype = "float", first.np_dtype
+            else:
+                kind = "int"
+                np_dtype = np.dtype("int64") if any(c.data.dtype == torch.int64 for c in cols) else np.dtype("int32")
+        if sync:
+            from ..dist import all_gather_object, world
+            if world()[0] > 1:
+                seen = all_gather_object((kind, str(np_dtype) if np_dtype is not None else None,
+                                          uni.tolist() if uni is not None else None))
+                kinds = {k for k, _, _ in seen if k is not None}
+                if len(kinds) > 1:
+                    raise TypeError(f"ranks disagree on the key type of a column group: {sorted(kinds)}")
+                kind = kinds.pop() if kinds else None
+                if kind == "str":
+                    uni = np.array(sorted(set(x for _, _, d in seen if d for x in d)), dtype=object)
+                elif kind == "int":
+                    np_dtype = np.dtype("int64") if any(d == "int64" for _, d, _ in seen) else np.dtype("int32")
+                elif kind == "float":
+                    np_dtype = np.dtype("float64") if any(d == "float64" for _, d, _ in seen) else np.dtype("float32")
+        if kind is None:                       # no rows anywhere
+            return cls("int", None, np.dtype("int64"))
+        return cls(kind, uni, np_dtype)
 
     def extend(self, cols: Sequence[Column]) -> "KeySpace":
         if self.kind != "str":
@@ -189,11 +217,14 @@ class ComboKeySpace:
         return len(cols) == 2 and all((not c.is_string) and c.data.dtype == torch.int32 for c in cols)
 
     @classmethod
-    def fit(cls, partitions: Sequence[Sequence[Column]]) -> "ComboKeySpace":
-        """partitions: per partition, the component columns (leaves)."""
-        ncomp = len(partitions[0])
+    def fit(cls, partitions: Sequence[Sequence[Column]], ncomp: Optional[int] = None) -> "ComboKeySpace":
+        """partitions: per partition, the component columns (leaves).  `ncomp` must be given
+        when a rank may hold no partition (every rank runs the same collectives)."""
+        ncomp = ncomp if ncomp is not None else len(partitions[0])
         spaces = [KeySpace.for_columns([p[j] for p in partitions]) for j in range(ncomp)]
-        if all(cls.can_pack_direct(p) for p in partitions):
+        # decided from the (rank-synchronised) spaces, so every rank takes the same path
+        if ncomp == 2 and all(s.kind == "int" and s.np_dtype == np.dtype("int32") for s in spaces) and \
+                all(cls.can_pack_direct(p) for p in partitions):
             return cls(spaces)
         self = cls(spaces, [], [])
         # stage j ranks component j; stage ncomp+k ranks the k-th running pair
@@ -217,10 +248,11 @@ class ComboKeySpace:
 
     @staticmethod
     def _rank_vocab(key_cols: Sequence[Column]):
+        from ..dist import global_merge
         agg = engine.HashAgg(0)
         for k in key_cols:
             agg.insert(k)
-        keys, _, _, _, _ = agg.export()
+        keys, _, _, _, _ = global_merge(agg)     # identical on every rank (single GPU: an export)
         keys, _ = torch.sort(keys)
         return engine.Vocab.from_arrays(keys), keys.cpu().numpy()
 

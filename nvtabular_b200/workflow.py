@@ -147,10 +147,8 @@ class Workflow:
 
     def transform(self, data):
         if isinstance(data, Dataset):
-            out = Dataset(data, _transform=self._transform_frame, base_dataset=data.base_dataset,
-                          schema=self._output_schema)
-            out._transform = self._transform_frame
-            return out
+            return Dataset(data, _transform=self._transform_frame, base_dataset=data.base_dataset,
+                           schema=self._output_schema)
         if isinstance(data, pd.DataFrame):
             if self._output_schema is None:
                 raise ValueError("no output schema")
