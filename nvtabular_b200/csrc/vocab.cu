@@ -859,7 +859,12 @@ static void pin_release(VocabScalars* p) {
   g_pin_free.push_back((int)(p - g_pin_slab));
 }
 
+// serialised: a host thread writing the artefact files and the thread running transform may
+// both ask for the scalars of the same vocabulary first
+static std::mutex g_fin_mu;
+
 static int vocab_finalize(nvtb_vocab* v) {
+  std::lock_guard<std::mutex> lk(g_fin_mu);
   if (!v->pending) return NVTB_OK;
   NVTB_CUDA_OK(cudaEventSynchronize(v->ev));
   const VocabScalars h = *v->h_sc;

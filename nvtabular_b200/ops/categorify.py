@@ -13,6 +13,7 @@ everything underneath is different:
   transform  one in-order probe pass per column (K5) — no merge, no sort back.
 """
 import os
+import threading
 import warnings
 from copy import deepcopy
 from typing import Dict, List, Optional
@@ -32,11 +33,35 @@ PAD_OFFSET, NULL_OFFSET, OOV_OFFSET = 0, 1, 2   # categorify.py:51-55
 EAGER_ARTIFACT_ROWS = 1 << 20                   # larger vocabularies are written lazily
 
 
+def _artifacts_mode() -> str:
+    """NVTB_ARTIFACTS = eager (default) | sync | lazy.
+
+    eager  every meta.<col>.parquet and the unique.<col>.parquet of every vocabulary up to
+           2^20 keys is written DURING fit, like the reference (whose only fitted state IS those
+           files) — by a pool of host threads, so that the pandas/pyarrow work overlaps the GPU
+           work still queued (the vocabulary builds of the large columns, the transform that
+           follows).  Reading a path (`op.categories[name]`), `Workflow.save`,
+           `set_storage_path` and `Workflow.wait_artifacts()` join the writes.
+    sync   the same files, written inline by the fitting thread.
+    lazy   nothing until a path is read."""
+    return os.environ.get("NVTB_ARTIFACTS", "eager").lower()
+
+
 def _artifacts_lazy() -> bool:
-    """NVTB_ARTIFACTS=lazy defers the unique./meta. parquet files until a path is read
-    (`op.categories[name]`, Workflow.save, set_storage_path).  Default: eager, like the
-    reference, whose only fitted state IS those files."""
-    return os.environ.get("NVTB_ARTIFACTS", "eager").lower() == "lazy"
+    return _artifacts_mode() == "lazy"
+
+
+_ARTIFACT_POOL = None
+_THREAD = threading.local()
+
+
+def _artifact_pool():
+    global _ARTIFACT_POOL
+    if _ARTIFACT_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _ARTIFACT_POOL = ThreadPoolExecutor(max_workers=int(os.environ.get("NVTB_ARTIFACT_THREADS", "8")),
+                                            thread_name_prefix="nvtb-artifacts")
+    return _ARTIFACT_POOL
 
 
 def _make_name(*args, sep="_"):
@@ -66,6 +91,13 @@ class FittedVocab:
         self.index_start = OOV_OFFSET + oov_count if index_start is None else index_start
         self.path = None
         self._written = False
+        self._future = None        # pending background write (NVTB_ARTIFACTS=eager)
+        # recorded right after the build was queued: a writer thread waits for THIS vocabulary
+        # only, on its own stream, instead of queueing behind the builds of later columns
+        self._ready = None
+        if torch.cuda.is_available():
+            self._ready = torch.cuda.Event()
+            self._ready.record()
 
     @property
     def n_kept(self):
@@ -103,22 +135,48 @@ class FittedVocab:
 
     def write(self, base_path, force=False):
         """categorify.py:731-822: unique.<name>.parquet (index = label) + meta.<name>.parquet."""
+        self.wait()
         self.path = "/".join([str(base_path), f"unique.{self.name}.parquet"])
-        if not force and _artifacts_lazy():
+        mode = _artifacts_mode()
+        if not force and mode == "lazy":
             self._written = False
             return self.path
         os.makedirs(base_path, exist_ok=True)
+        if force or mode == "sync" or not torch.cuda.is_available():
+            self._write_now(base_path, force)
+        else:
+            self._written = False
+            self._future = _artifact_pool().submit(self._write_in_thread, base_path, torch.cuda.current_device())
+        return self.path
+
+    def _write_in_thread(self, base_path, dev):
+        torch.cuda.set_device(dev)
+        side = getattr(_THREAD, "stream", None)
+        if side is None or side.device.index != dev:
+            side = _THREAD.stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(side):
+            if self._ready is not None:
+                side.wait_event(self._ready)
+            self._write_now(base_path, False)
+
+    def _write_now(self, base_path, force):
         meta_path = "/".join([str(base_path), f"meta.{self.name}.parquet"])
         self.meta_frame().to_parquet(meta_path)
         if force or self.vocab.n_kept <= EAGER_ARTIFACT_ROWS:
             df = self.unique_frame()
             if self.vocab.n_total == 0:   # categorify.py:1318-1324: empty input -> a single null row
                 df = pd.DataFrame({n: pd.Series([None], dtype=object) for n in self.key_names})
-            df.to_parquet(self.path, compression=None)
+            df.to_parquet("/".join([str(base_path), f"unique.{self.name}.parquet"]), compression=None)
             self._written = True
-        return self.path
+
+    def wait(self):
+        """join a pending background write (re-raises what it raised)"""
+        fut, self._future = self._future, None
+        if fut is not None:
+            fut.result()
 
     def ensure_written(self):
+        self.wait()
         if self.path is not None and not self._written:
             self.write(os.path.dirname(self.path), force=True)
 
@@ -442,8 +500,14 @@ class Categorify(StatOperator):
             self.categories[name] = fv.path
             self.categories.fitted[name] = fv
 
+    def wait_artifacts(self):
+        """join the background writes of this op's vocabulary files (NVTB_ARTIFACTS=eager)"""
+        for fv in self.categories.fitted.values():
+            fv.wait()
+
     def set_storage_path(self, new_path, copy=False):
         for name, fv in self.categories.fitted.items():
+            fv.wait()
             if copy:
                 fv.write(os.path.join(new_path, "categories"), force=True)
             else:

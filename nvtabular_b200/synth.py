@@ -111,3 +111,20 @@ def movielens_frame(rows: int, seed: int = 4321, device="cuda", rank: int = 0) -
     movie = scatter_ids(power_law_ids(rows, 60_000, g, device, 0.5))
     rating = (torch.randint(1, 11, (rows,), generator=g, device=device).to(torch.float32)) * 0.5
     return DeviceFrame({"userId": Column(user), "movieId": Column(movie), "rating": Column(rating)})
+
+
+def hashbucket_frame(rows: int, ncols: int = 40, n_ids: int = 100_000_000, seed: int = 777, device="cuda",
+                     rank: int = 0) -> DeviceFrame:
+    """BASELINE.json configs[4]: `ncols` int64 key columns, keys uniform over
+    `n_ids` ids mixed through a 64-bit bijection (odd multiply, xor-shift, odd multiply — wrapping
+    int64 arithmetic), no nulls.  Input of HashBucket(num_buckets=2**20)."""
+    cols: Dict[str, Column] = {}
+    m1, m2 = -7046029254386353131, -4658895280553007687      # 0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9 as int64
+    for j in range(ncols):
+        g = _gen(seed + j + 10_000 * rank, device)
+        k = torch.randint(0, n_ids, (rows,), generator=g, device=device, dtype=torch.int64)
+        k.mul_(m1)
+        k.bitwise_xor_((k >> 29) & ((1 << 35) - 1))       # logical shift: a bijection
+        k.mul_(m2)
+        cols[f"K{j + 1}"] = Column(k)
+    return DeviceFrame(cols)

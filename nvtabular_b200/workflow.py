@@ -114,6 +114,17 @@ class Workflow:
                 fitted.add(id(n))
             stat_nodes = [n for n in stat_nodes if id(n) not in fitted]
         self.fit_schema(dataset.schema)
+        # the reference's fit returns with its vocabulary files on disk: join the writer threads
+        # (they have been working while the GPU ran the vocabulary builds still queued)
+        if not os.environ.get("NVTB_ARTIFACTS_NOWAIT"):
+            self.wait_artifacts()
+        return self
+
+    def wait_artifacts(self) -> "Workflow":
+        """Join the background writes of every op's artefact files (NVTB_ARTIFACTS=eager)."""
+        for n in self.output_node.topo_order():
+            if n.kind == "op" and hasattr(n.op, "wait_artifacts"):
+                n.op.wait_artifacts()
         return self
 
     def fit_schema(self, input_schema: Schema) -> "Workflow":

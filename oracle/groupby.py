@@ -143,6 +143,49 @@ def add_fold(n, kfold, fold_seed=None):
     return state.choice(np.arange(kfold, dtype=typ), n)
 
 
+def te_transform_part(p, groups, tables, y_mean, target_cols, kfold, p_smooth, out_dtype=None, sep="_",
+                      fold_name="__fold__"):
+    """TargetEncoding.transform of ONE partition that already carries its fold column
+    (target_encoding.py:301-424)."""
+    tmp = "__tmp__"
+    p = p.copy(deep=False)
+    p[tmp] = np.arange(len(p), dtype="int32")
+    new_df = None
+    for g in groups:
+        out_col = [f"TE_{_make_name(*g, sep=sep)}_{x}" for x in target_cols]
+        agg_all = tables[_make_name(*g, sep=sep)].copy()
+        agg_all.columns = g + ["count_y_all"] + [x + "_sum_y_all" for x in target_cols]
+        if kfold > 1:
+            cols = [fold_name] + g
+            agg_f = tables[_make_name(*cols, sep=sep)].copy()
+            agg_f.columns = cols + ["count_y"] + [x + "_sum_y" for x in target_cols]
+            agg_f = agg_f.merge(agg_all, on=g, how="left")
+            agg_f["count_y_all"] = agg_f["count_y_all"] - agg_f["count_y"]
+            for i, x in enumerate(target_cols):
+                agg_f[x + "_sum_y_all"] = agg_f[x + "_sum_y_all"] - agg_f[x + "_sum_y"]
+                agg_f[out_col[i]] = (agg_f[x + "_sum_y_all"] + p_smooth * y_mean[x]) / (
+                    agg_f["count_y_all"] + p_smooth)
+            agg_f = agg_f.drop(["count_y_all", "count_y"] + [x + "_sum_y" for x in target_cols]
+                               + [x + "_sum_y_all" for x in target_cols], axis=1)
+            tran = p[cols + [tmp]].merge(agg_f, on=cols, how="left")
+        else:
+            cols = g
+            for i, x in enumerate(target_cols):
+                agg_all[out_col[i]] = (agg_all[x + "_sum_y_all"] + p_smooth * y_mean[x]) / (
+                    agg_all["count_y_all"] + p_smooth)
+            agg_all = agg_all.drop(["count_y_all"] + [x + "_sum_y_all" for x in target_cols], axis=1)
+            tran = p[cols + [tmp]].merge(agg_all, on=cols, how="left")
+        for i, x in enumerate(target_cols):
+            tran[out_col[i]] = tran[out_col[i]].fillna(y_mean[x])
+        if out_dtype is not None:
+            tran[out_col] = tran[out_col].astype(out_dtype)
+        tran = tran.sort_values(tmp, ignore_index=True).drop(columns=cols + [tmp])
+        tran.index = p.index
+        tran = tran.astype(out_dtype or np.float32)
+        new_df = tran if new_df is None else pd.concat([new_df, tran], axis=1)
+    return new_df
+
+
 def target_encoding(partitions, cat_groups, target_cols: List[str], kfold=3, fold_seed=42,
                     p_smooth=20, out_dtype=None, target_mean=None, sep="_"):
     """TargetEncoding fit + transform on a list of pandas partitions
@@ -170,43 +213,6 @@ def target_encoding(partitions, cat_groups, target_cols: List[str], kfold=3, fol
         if kfold > 1:
             fg = [fold_name] + g
             tables[_make_name(*fg, sep=sep)] = groupby_stats(parts, fg, target_cols, ["count", "sum"], sep)
-    outs = []
-    for p in parts:
-        tmp = "__tmp__"
-        p = p.copy(deep=False)
-        p[tmp] = np.arange(len(p), dtype="int32")
-        new_df = None
-        for g in groups:
-            out_col = [f"TE_{_make_name(*g, sep=sep)}_{x}" for x in target_cols]
-            agg_all = tables[_make_name(*g, sep=sep)].copy()
-            agg_all.columns = g + ["count_y_all"] + [x + "_sum_y_all" for x in target_cols]
-            if kfold > 1:
-                cols = [fold_name] + g
-                agg_f = tables[_make_name(*cols, sep=sep)].copy()
-                agg_f.columns = cols + ["count_y"] + [x + "_sum_y" for x in target_cols]
-                agg_f = agg_f.merge(agg_all, on=g, how="left")
-                agg_f["count_y_all"] = agg_f["count_y_all"] - agg_f["count_y"]
-                for i, x in enumerate(target_cols):
-                    agg_f[x + "_sum_y_all"] = agg_f[x + "_sum_y_all"] - agg_f[x + "_sum_y"]
-                    agg_f[out_col[i]] = (agg_f[x + "_sum_y_all"] + p_smooth * y_mean[x]) / (
-                        agg_f["count_y_all"] + p_smooth)
-                agg_f = agg_f.drop(["count_y_all", "count_y"] + [x + "_sum_y" for x in target_cols]
-                                   + [x + "_sum_y_all" for x in target_cols], axis=1)
-                tran = p[cols + [tmp]].merge(agg_f, on=cols, how="left")
-            else:
-                cols = g
-                for i, x in enumerate(target_cols):
-                    agg_all[out_col[i]] = (agg_all[x + "_sum_y_all"] + p_smooth * y_mean[x]) / (
-                        agg_all["count_y_all"] + p_smooth)
-                agg_all = agg_all.drop(["count_y_all"] + [x + "_sum_y_all" for x in target_cols], axis=1)
-                tran = p[cols + [tmp]].merge(agg_all, on=cols, how="left")
-            for i, x in enumerate(target_cols):
-                tran[out_col[i]] = tran[out_col[i]].fillna(y_mean[x])
-            if out_dtype is not None:
-                tran[out_col] = tran[out_col].astype(out_dtype)
-            tran = tran.sort_values(tmp, ignore_index=True).drop(columns=cols + [tmp])
-            tran.index = p.index
-            tran = tran.astype(out_dtype or np.float32)
-            new_df = tran if new_df is None else pd.concat([new_df, tran], axis=1)
-        outs.append(new_df)
+    outs = [te_transform_part(p, groups, tables, y_mean, target_cols, kfold, p_smooth, out_dtype, sep, fold_name)
+            for p in parts]
     return outs, tables, y_mean

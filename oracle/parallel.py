@@ -112,3 +112,122 @@ def run_criteo_workflow(df: pd.DataFrame, cats: List[str], conts: List[str], wor
         shutil.rmtree(tmp, ignore_errors=True)
         _VOCAB_CACHE.clear()
     return t1 - t0, t2 - t1, vocabs, means, stds
+
+
+# ---------------------------------------------------------------------------------------
+# C5: HashBucket over many key columns (nvtabular/ops/hash_bucket.py:86-100)
+# ---------------------------------------------------------------------------------------
+_HB = {}
+
+
+def _hb_task(args):
+    j, lo, hi = args
+    from .hashing import hash_bucket
+    out = hash_bucket(_HB["cols"][j][lo:hi], _HB["nb"])
+    return int(out[:16].sum())          # the labels stay in the worker; a checksum comes back
+
+
+def run_hashbucket(cols: List[np.ndarray], num_buckets: int, workers: int = 1) -> float:
+    """hash_series(col) % num_buckets for every column, row ranges spread over `workers` forked
+    processes (the arrays are inherited, not pickled).  Returns seconds."""
+    _HB.clear()
+    _HB.update(cols=cols, nb=num_buckets)
+    n = len(cols[0])
+    workers = max(1, workers)
+    per = max(1, -(-workers // len(cols)))                 # row ranges per column
+    chunk = -(-n // per)
+    tasks = [(j, lo, min(n, lo + chunk)) for j in range(len(cols)) for lo in range(0, n, chunk)]
+    pool = mp.get_context("fork").Pool(workers) if workers > 1 else None
+    try:
+        t0 = time.perf_counter()
+        if pool:
+            pool.map(_hb_task, tasks, chunksize=1)
+        else:
+            for t in tasks:
+                _hb_task(t)
+        return time.perf_counter() - t0
+    finally:
+        if pool:
+            pool.close()
+            pool.join()
+
+
+# ---------------------------------------------------------------------------------------
+# C4: JoinGroupby + TargetEncoding on a ratings table
+# (nvtabular/ops/join_groupby.py:140-217, target_encoding.py:171-439)
+# ---------------------------------------------------------------------------------------
+_ML = {}
+
+
+def _ml_fit_part(i):
+    from .groupby import _top_level
+    p = _PARTS[i]
+    out = {}
+    for g in _ML["groups"]:
+        out[("jg",) + tuple(g)] = _top_level(p, g, _ML["conts"], _ML["stats"])
+        out[("te",) + tuple(g)] = _top_level(p, g, _ML["targets"], ["count", "sum"])
+        fg = ["__fold__"] + g
+        out[("te",) + tuple(fg)] = _top_level(p, fg, _ML["targets"], ["count", "sum"])
+    return out, chunkwise_moments(p[_ML["targets"]])
+
+
+def _ml_transform_part(i):
+    from .groupby import join_groupby_transform, te_transform_part
+    p = _PARTS[i]
+    a = join_groupby_transform(p, _ML["groups"], _ML["jg_tables"])
+    b = te_transform_part(p, _ML["groups"], _ML["te_tables"], _ML["y_mean"], _ML["targets"], _ML["kfold"],
+                          _ML["p_smooth"])
+    return float(a.iloc[:16].to_numpy(dtype="float64").sum() + b.iloc[:16].to_numpy(dtype="float64").sum())
+
+
+def run_movielens_workflow(df: pd.DataFrame, workers: int = 1, kfold: int = 5, p_smooth: float = 20.0,
+                           fold_seed: int = 42):
+    """["userId","movieId",["userId","movieId"]] >> JoinGroupby(cont_cols=["rating"],
+    stats=[count,sum,mean,std]) + TargetEncoding("rating", kfold, p_smooth): per-partition partial
+    group-bys in parallel, merged by the parent (_bottom_level), transform in parallel over the
+    partitions (the tables reach the forked workers through module state).  Returns
+    (seconds_fit, seconds_transform)."""
+    global _PARTS
+    from .groupby import _bottom_level, _make_name, add_fold
+    n = len(df)
+    workers = max(1, min(workers, max(1, n // 50_000)))
+    chunk = -(-n // workers)
+    parts = []
+    for i in range(0, n, chunk):
+        p = df.iloc[i:i + chunk].reset_index(drop=True)
+        p["__fold__"] = add_fold(len(p), kfold, fold_seed)
+        parts.append(p)
+    _PARTS = parts
+    groups = [["userId"], ["movieId"], ["userId", "movieId"]]
+    stats = ["count", "sum", "mean", "std"]
+    _ML.clear()
+    _ML.update(groups=groups, conts=["rating"], targets=["rating"], stats=stats, kfold=kfold, p_smooth=p_smooth)
+    idx = list(range(len(parts)))
+    t0 = time.perf_counter()
+    pool = mp.get_context("fork").Pool(workers) if workers > 1 else None
+    try:
+        res = pool.map(_ml_fit_part, idx) if pool else [_ml_fit_part(i) for i in idx]
+    finally:
+        if pool:
+            pool.close()
+            pool.join()
+    jg_tables, te_tables = {}, {}
+    for g in groups:
+        jg_tables[_make_name(*g)] = _bottom_level([r[0][("jg",) + tuple(g)] for r in res], g, ["rating"], stats)
+        te_tables[_make_name(*g)] = _bottom_level([r[0][("te",) + tuple(g)] for r in res], g, ["rating"],
+                                                  ["count", "sum"])
+        fg = ["__fold__"] + g
+        te_tables[_make_name(*fg)] = _bottom_level([r[0][("te",) + tuple(fg)] for r in res], fg, ["rating"],
+                                                   ["count", "sum"])
+    stats_m = finalize_moments(tree_node_moments([r[1] for r in res]))
+    _ML.update(jg_tables=jg_tables, te_tables=te_tables, y_mean={"rating": float(stats_m["mean"].loc["rating"])})
+    t1 = time.perf_counter()
+    pool = mp.get_context("fork").Pool(workers) if workers > 1 else None     # forked AFTER the tables exist
+    try:
+        _ = pool.map(_ml_transform_part, idx) if pool else [_ml_transform_part(i) for i in idx]
+    finally:
+        if pool:
+            pool.close()
+            pool.join()
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1

@@ -7,7 +7,7 @@ import bench
 rows = 1 << 26
 dev = torch.device("cuda", 0)
 frame = criteo_frame(rows, device="cuda")
-wf = bench.build_workflow(nvt, "/tmp/nvtb_e2e")
+wf = bench.build_workflow(nvt, "criteo", "/tmp/nvtb_e2e")
 host = bench.host_partitions(frame, 8)
 del frame
 torch.cuda.synchronize()
