@@ -234,8 +234,12 @@ def run_step_e2e(nvt, wf, host_parts, out_host, fit=True):
     tds = wf.transform(ds)
     res = tds.to_host(out_host if out_host else None)
     if trace:
-        sys.stderr.write("[bench dump] e2e step: fit %.1f ms, transform+to_host %.1f ms\n"
-                         % ((t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3))
+        ms = torch.cuda.memory_stats()
+        sys.stderr.write("[bench dump] e2e step: fit %.1f ms, transform+to_host %.1f ms; cudaMalloc %d cudaFree %d "
+                         "retries %d reserved %.1f GB\n"
+                         % ((t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3, ms.get("num_device_alloc", -1),
+                            ms.get("num_device_free", -1), ms.get("num_alloc_retries", -1),
+                            ms.get("reserved_bytes.all.current", 0) / 1e9))
     return ds.h2d_bytes, tds.d2h_bytes, res
 
 
@@ -296,9 +300,9 @@ def workload_config(args, world, rows):
                 "algorithmic_bytes_per_row": ALGO_BYTES["criteo32" if args.int32_outputs else "criteo"],
                 "cache": "inputs (%.1f GB/GPU) larger than L2; no explicit flush" % (rows * 160.9 / 1e9),
                 "artifacts": {"eager": "library default: every meta.<col>.parquet and the unique.<col>.parquet of "
-                                       "every vocabulary up to 2^20 keys written during fit by host threads, "
-                                       "joined before fit returns; larger vocabulary files on first read",
-                              "sync": "same files, written inline", "lazy": "deferred until read"}[args.artifacts],
+                                       "every vocabulary up to 2^20 keys written inside fit (under the GPU's "
+                                       "builds of the large vocabularies); larger vocabulary files on first read",
+                              "lazy": "deferred until read"}[args.artifacts],
                 "parallelism": f"row-sharded x{world}, key-hash owner merge over NCCL" if world > 1 else "single GPU"}
     if args.workload == "hashbucket":
         return {"workload": "BASELINE.json configs[4]: 40 int64 key columns, keys uniform over 1e8 ids through a "
@@ -512,14 +516,15 @@ def main():
     ap.add_argument("--parts", type=int, default=4, help="device-resident partitions the table is cut into")
     ap.add_argument("--profile-rows", type=int, default=4_370_000_000,
                     help="row count the categorical cardinalities are scaled to (4.37e9 = the full Criteo-1TB profile)")
-    ap.add_argument("--e2e-rows", type=int, default=0, help="rows per GPU per e2e step (default: the same table)")
-    ap.add_argument("--e2e-parts", type=int, default=0, help="host partitions per e2e step (default: 8 per 2^26 rows)")
+    ap.add_argument("--e2e-rows", type=int, default=0,
+                    help="rows per GPU per e2e step (default: the first min(rows, 2^27) rows of the same table)")
+    ap.add_argument("--e2e-parts", type=int, default=0, help="host partitions per e2e step (default: 2^23 rows each)")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the bounded CPU sample")
     ap.add_argument("--int32-outputs", action="store_true", help="Categorify(dtype=int32), Normalize(float32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gate", action="store_true", help="skip the parity gate")
-    ap.add_argument("--artifacts", default="eager", choices=["eager", "sync", "lazy"],
+    ap.add_argument("--artifacts", default="eager", choices=["eager", "lazy"],
                     help="NVTB_ARTIFACTS for the timed steps (eager = library default)")
     ap.add_argument("--sweep", default="", help="hashbucket: comma-separated row counts for the roofline curve")
     ap.add_argument("--pyprofile", action="store_true", help="cProfile one extra step to stderr")
@@ -698,7 +703,7 @@ def main():
     artifact_legs = None
     if wl == "criteo" and world == 1 and not args.no_e2e:
         artifact_legs = {}
-        for mode in ("lazy", "sync"):
+        for mode in ("lazy", "eager"):
             if mode == args.artifacts:
                 continue
             try:
@@ -713,23 +718,25 @@ def main():
     # ---------------- end to end from pinned host buffers ---------------------------
     e2e = None
     if not args.no_e2e:
-        e_rows = args.e2e_rows or rows
-        e_parts = args.e2e_parts or max(8, (e_rows + (1 << 23) - 1) >> 23)
-        if e_rows == rows:
-            src = frame
-            host = []
-            per = max(1, e_parts // len(frame))
-            for p in frame:
-                host += host_partitions(p, per)
-        else:
-            src = make_table(wl, e_rows, dev, rank, args.profile_rows)
-            host = host_partitions(src, e_parts)
+        # host footprint: the pinned-memory allocator rounds every buffer up to a power of two, and
+        # the 1-GPU box's cgroup holds 200 GiB — partitions of exactly 2^23 rows (32 / 64 MiB
+        # buffers) and at most 2^27 rows per GPU keep a step at ~64 GB of pinned memory
+        e_rows = args.e2e_rows or min(rows, 1 << 27)
+        e_parts = args.e2e_parts or max(1, (e_rows + (1 << 23) - 1) >> 23)
+        src = table.slice_rows(0, e_rows) if e_rows <= rows else make_table(wl, e_rows, dev, rank, args.profile_rows)
+        host = host_partitions(src, e_parts)
         del src
         table = None
         # the device-resident table and the allocator blocks cached by the timed region above
         # are not part of the e2e leg: it starts from host buffers and a clean device pool
         frame = None
+        import gc
+        gc.collect()
         torch.cuda.empty_cache()
+        if os.environ.get("NVTB_BENCH_DUMP"):
+            free, tot = torch.cuda.mem_get_info()
+            sys.stderr.write("[bench dump] before e2e: torch allocated %.1f GB, reserved %.1f GB, device free %.1f of %.1f GB\n"
+                             % (torch.cuda.memory_allocated() / 1e9, torch.cuda.memory_reserved() / 1e9, free / 1e9, tot / 1e9))
         out_host = None
         # W >= 3 warm-up steps here too: the first e2e step pins the result buffers (seconds),
         # the second still grows the device allocator's pools

@@ -116,6 +116,16 @@ int nvtb_minmax_apply(const nvtb_col_t* cols_host, int ncols, int64_t n,
                       const double* maxs_host, void* const* out_host,
                       int out_dtype, void* stream);
 
+/* Clip (reference nvtabular/ops/clip.py:46-53) and Clip + LogOp (ops/logop.py:47-56) in one
+ * pass, with an upstream FillMissing fused in (fill_vals[c] NaN = none): x = fill if null;
+ * x = max(x, min_vals[c]); x = min(x, max_vals[c]) (NaN bound / NULL array = none);
+ * take_log == 0: out[c] has the column's own dtype; take_log != 0: out[c] (out_dtype float32 |
+ * float64) = log(x cast to out_dtype + 1).  Rows that stay null are written as 0 / NaN. */
+int nvtb_cliplog_apply(const nvtb_col_t* cols, int ncols, int64_t n,
+                       const double* fill_vals, const double* min_vals,
+                       const double* max_vals, int take_log, void* const* out,
+                       int out_dtype, void* stream);
+
 /* ---- HashBucket ---------------------------------------------------------
  * dispatch.hash_series(col) % nb  (reference nvtabular/ops/hash_bucket.py:
  * 86-100, nvtabular/ops/categorify.py:1837-1852).  The hash is the value-only
@@ -198,6 +208,31 @@ int nvtb_hashagg_export(nvtb_hashagg_t* h, int64_t* keys_out,
  * nvtabular/ops/categorify.py:955-1137 for the C20/C1/C22/C10 class of Criteo columns. */
 int nvtb_hashagg_mode(nvtb_hashagg_t* h, int* mode_host);
 
+/* ---- sorted-pair primitives of the cross-GPU vocabulary merge --------------
+ * A high-cardinality column is exchanged between GPUs as key-ordered packed pairs
+ * word = (uint32)(key ^ 2^31) << 32 | (uint32)count (unsigned order of the word == key order),
+ * split by KEY RANGE (the local accumulator is already grouped by owner: no partition pass),
+ * merged by the owner, ordered by count on the owner, and the owners' count-ordered shards
+ * are interleaved into the global (count desc, key asc) order group by group.  Replaces the
+ * dask tree + shared-filesystem hop of reference nvtabular/ops/categorify.py:1036-1049,
+ * 1399-1540.  The collectives themselves are issued by the host (torch.distributed / NCCL). */
+/* make the handle a sorted accumulator (no-op if it is one); NVTB_ESTATE when the handle holds
+ * int64 keys, payload columns or >= 2^32 rows */
+int nvtb_hashagg_to_sorted(nvtb_hashagg_t* h, void* stream);
+/* copy the packed pairs of a sorted accumulator (key order) to `out` (may be NULL: size query) */
+int nvtb_hashagg_export_packed(nvtb_hashagg_t* h, uint64_t* out, int64_t* n_host, void* stream);
+/* out_dev[j] = number of pairs whose unsigned key is < bounds_dev[j]  (the split points of the
+ * key-range exchange) */
+int nvtb_pairs_lower_bounds(const uint64_t* pairs, int64_t n, const uint32_t* bounds_dev, int m,
+                            int64_t* out_dev, void* stream);
+/* merge two key-sorted, key-unique pair arrays adding the counts of equal keys (the owner-side
+ * _mid_level_groupby, categorify.py:1054-1070); out holds na + nb pairs; synchronises */
+int nvtb_pairs_merge(const uint64_t* a, int64_t na, const uint64_t* b, int64_t nb, uint64_t* out,
+                     int64_t* n_out_host, void* stream);
+/* copy nseg contiguous segments [seg_src[s], seg_src[s+1]) of src to dst + seg_dst[s] */
+int nvtb_segment_copy_u64(const uint64_t* src, uint64_t* dst, const int64_t* seg_src_dev,
+                          const int64_t* seg_dst_dev, int nseg, int64_t n, void* stream);
+
 /* Stable LSD radix sort of device arrays by bits [lo_bit, hi_bit) of every element
  * (csrc/radix.cuh; ascending, or descending on that bit field).  data/tmp: n elements
  * each, 16-byte aligned; the result ends in data (*result_in_tmp_host = 0) or tmp (= 1).
@@ -272,6 +307,11 @@ int nvtb_vocab_build_from_hashagg(nvtb_vocab_t** out, nvtb_hashagg_t* h,
                                   int64_t freq_threshold, int64_t max_size,
                                   int64_t num_buckets, int key_bits, int64_t size_bound,
                                   void* stream);
+/* the same from packed pairs that are ALREADY in (count desc, key asc) order (assembled by the
+ * cross-GPU merge); the array is copied */
+int nvtb_vocab_build_from_pairs(nvtb_vocab_t** out, const uint64_t* ordered_pairs, int64_t n,
+                                int64_t null_size, int64_t freq_threshold, int64_t max_size,
+                                int64_t num_buckets, void* stream);
 int nvtb_vocab_from_arrays(nvtb_vocab_t** out, const int64_t* keys,
                            const int64_t* sizes, int64_t n, void* stream);
 int nvtb_vocab_destroy(nvtb_vocab_t* v);
@@ -315,6 +355,27 @@ int nvtb_groupstats_gather(const nvtb_groupstats_t* g,
                            const double* miss_vals_host,
                            void* const* out_host, const int* out_dtypes_host,
                            void* stream);
+
+/* ---- inference-time transforms on HOST arrays --------------------------------------------
+ * The twin of the reference's pybind11 module nvtabular_cpp.inference
+ * (cpp/nvtabular/inference/categorify.cc:31-347, fill.cc:32-124; bound at
+ * nvtabular/ops/categorify.py:602-609, ops/fill.py:59-65): dict-of-numpy requests of a serving
+ * process are encoded by probing a host table of the kept keys (built once from the device
+ * vocabulary) with a few host threads — a serving batch is too small to pay for a PCIe round
+ * trip.  Labels are identical to nvtb_encode_apply's. */
+typedef struct nvtb_infer_vocab nvtb_infer_vocab_t;
+/* label = first_label + position of the key in keys_host */
+int nvtb_infer_vocab_create(nvtb_infer_vocab_t** out, const int64_t* keys_host, int64_t n);
+int nvtb_infer_vocab_from_device(nvtb_infer_vocab_t** out, const nvtb_vocab_t* v, void* stream);
+int nvtb_infer_vocab_destroy(nvtb_infer_vocab_t* v);
+/* keys_host: int32 | int64 [n]; validity_host: Arrow bitmask or NULL; labels_out_host: int32 |
+ * int64 [n]; n_threads <= 0: hardware concurrency (one thread per 16 Ki rows at most) */
+int nvtb_infer_categorify_host(const nvtb_infer_vocab_t* v, const void* keys_host, int key_dtype,
+                               const uint8_t* validity_host, int64_t n, int64_t null_label,
+                               int64_t oov_label, int64_t first_label, uint64_t num_buckets,
+                               void* labels_out_host, int out_dtype, int n_threads);
+/* FillMissing in place on a host float32 / float64 array (NaN -> fill); integer arrays pass */
+int nvtb_infer_fill_host(void* data_host, int dtype, int64_t n, double fill);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "nvtb_fill_apply": (c_int, [POINTER(nvtb_col_t), c_int, c_int64, POINTER(c_double), POINTER(c_void_p), POINTER(c_void_p), c_void_p]),
     "nvtb_normalize_apply": (c_int, [POINTER(nvtb_col_t), c_int, c_int64, POINTER(c_double), POINTER(c_double), POINTER(c_double), POINTER(c_void_p), c_int, c_void_p]),
     "nvtb_minmax_apply": (c_int, [POINTER(nvtb_col_t), c_int, c_int64, POINTER(c_double), POINTER(c_double), POINTER(c_double), POINTER(c_void_p), c_int, c_void_p]),
+    "nvtb_cliplog_apply": (c_int, [POINTER(nvtb_col_t), c_int, c_int64, POINTER(c_double), POINTER(c_double), POINTER(c_double), c_int, POINTER(c_void_p), c_int, c_void_p]),
     "nvtb_hash_bucket_apply": (c_int, [POINTER(nvtb_col_t), c_int, c_int64, c_uint64, c_int64, c_void_p, c_int, c_void_p]),
     "nvtb_hash_values": (c_int, [POINTER(nvtb_col_t), c_int64, c_void_p, c_void_p]),
     "nvtb_hashagg_create": (c_int, [POINTER(c_void_p), c_int, c_int64]),
@@ -53,6 +54,11 @@ _SIGNATURES = {
     "nvtb_hashagg_size": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p]),
     "nvtb_hashagg_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double), c_void_p]),
     "nvtb_hashagg_mode": (c_int, [c_void_p, POINTER(c_int)]),
+    "nvtb_hashagg_to_sorted": (c_int, [c_void_p, c_void_p]),
+    "nvtb_hashagg_export_packed": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_void_p]),
+    "nvtb_pairs_lower_bounds": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
+    "nvtb_pairs_merge": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, POINTER(c_int64), c_void_p]),
+    "nvtb_segment_copy_u64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "nvtb_radix_sort_u32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, POINTER(c_int), c_void_p]),
     "nvtb_radix_sort_u64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, POINTER(c_int), c_void_p]),
     "nvtb_partition_by_owner": (c_int, [c_void_p, c_int64, c_int, c_void_p, POINTER(c_int64), c_void_p]),
@@ -62,11 +68,17 @@ _SIGNATURES = {
     "nvtb_pack_keys2": (c_int, [POINTER(nvtb_col_t), POINTER(nvtb_col_t), c_int64, c_void_p, c_void_p, c_void_p]),
     "nvtb_vocab_build": (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int64, c_void_p]),
     "nvtb_vocab_build_from_hashagg": (c_int, [POINTER(c_void_p), c_void_p, c_int64, c_int64, c_int64, c_int, c_int64, c_void_p]),
+    "nvtb_vocab_build_from_pairs": (c_int, [POINTER(c_void_p), c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "nvtb_vocab_from_arrays": (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_int64, c_void_p]),
     "nvtb_vocab_destroy": (c_int, [c_void_p]),
     "nvtb_vocab_info": (c_int, [c_void_p, POINTER(nvtb_vocab_info_t)]),
     "nvtb_vocab_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "nvtb_encode_apply": (c_int, [c_void_p, POINTER(nvtb_col_t), c_int64, c_int64, c_int64, c_int64, c_uint64, POINTER(nvtb_col_t), c_int, c_void_p, c_int, c_void_p]),
+    "nvtb_infer_vocab_create": (c_int, [POINTER(c_void_p), c_void_p, c_int64]),
+    "nvtb_infer_vocab_from_device": (c_int, [POINTER(c_void_p), c_void_p, c_void_p]),
+    "nvtb_infer_vocab_destroy": (c_int, [c_void_p]),
+    "nvtb_infer_categorify_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_uint64, c_void_p, c_int, c_int]),
+    "nvtb_infer_fill_host": (c_int, [c_void_p, c_int, c_int64, c_double]),
     "nvtb_groupstats_create": (c_int, [POINTER(c_void_p), c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p]),
     "nvtb_groupstats_destroy": (c_int, [c_void_p]),
     "nvtb_groupstats_gather": (c_int, [c_void_p, POINTER(nvtb_col_t), c_int64, POINTER(c_int), c_int, POINTER(c_double), POINTER(c_void_p), POINTER(c_int), c_void_p]),

@@ -195,7 +195,7 @@ __global__ void moments_init_kernel(double* acc, int ncols) {
 // --------------------------------------------------------------------------
 // K2: transforms
 // --------------------------------------------------------------------------
-enum { OP_FILL = 0, OP_NORMALIZE = 1, OP_MINMAX = 2 };
+enum { OP_FILL = 0, OP_NORMALIZE = 1, OP_MINMAX = 2, OP_CLIP = 3, OP_CLIPLOG = 4 };
 
 template <typename T, typename OutT, int OP>
 __device__ __forceinline__ void transform_column(const ColBatch& cb, int c,
@@ -250,6 +250,32 @@ __device__ __forceinline__ void transform_column(const ColBatch& cb, int c,
                         if (divide) r = r / p1;
                         return (OutT)r;
                       });
+  } else if constexpr (OP == OP_CLIP || OP == OP_CLIPLOG) {
+    // Clip (reference nvtabular/ops/clip.py:46-53): values below p0 become p0, above p1 become
+    // p1 (NaN bound = none; nulls stay nulls unless an upstream FillMissing is fused in), then
+    // for OP_CLIPLOG LogOp (ops/logop.py:47-56): log(x.astype(out dtype) + 1) in that dtype —
+    // evaluated in fp64 and rounded once, i.e. the correctly rounded value
+    const double lo = cb.p0[c], hi = cb.p1[c];
+    const bool has_lo = lo == lo, has_hi = hi == hi;
+    const T lo_t = has_lo ? (T)lo : (T)0, hi_t = has_hi ? (T)hi : (T)0;
+    map_rows<T, OutT>(data, mask, out, n, aligned,
+                      [&](int64_t, T x, bool valid) -> OutT {
+                        bool isnull = !valid;
+                        if constexpr (std::is_floating_point<T>::value)
+                          isnull = isnull || (x != x);
+                        if (isnull) {
+                          if (!filling) return out_null;
+                          x = fill_t;
+                        }
+                        if (has_lo && x < lo_t) x = lo_t;
+                        if (has_hi && x > hi_t) x = hi_t;
+                        if constexpr (OP == OP_CLIPLOG) {
+                          const OutT xo = (OutT)x + (OutT)1;
+                          return (OutT)log((double)xo);
+                        } else {
+                          return (OutT)x;
+                        }
+                      });
   } else {  // OP_MINMAX: p0 = min, p1 = max
     const CT dif = p1 - p0;
     map_rows<T, OutT>(data, mask, out, n, aligned,
@@ -290,6 +316,19 @@ fill_kernel(ColBatch cb, int64_t n) {
     case NVTB_I64: transform_column<int64_t, int64_t, OP_FILL>(cb, c, n); break;
     case NVTB_F32: transform_column<float, float, OP_FILL>(cb, c, n); break;
     default:       transform_column<double, double, OP_FILL>(cb, c, n); break;
+  }
+}
+
+// Clip keeps the dtype, so OutT == T per column (nulls of an unfilled integer column come out
+// as 0 under an unchanged validity mask)
+__global__ void __launch_bounds__(kThreads)
+clip_kernel(ColBatch cb, int64_t n) {
+  const int c = blockIdx.y;
+  switch (cb.dtype[c]) {
+    case NVTB_I32: transform_column<int32_t, int32_t, OP_CLIP>(cb, c, n); break;
+    case NVTB_I64: transform_column<int64_t, int64_t, OP_CLIP>(cb, c, n); break;
+    case NVTB_F32: transform_column<float, float, OP_CLIP>(cb, c, n); break;
+    default:       transform_column<double, double, OP_CLIP>(cb, c, n); break;
   }
 }
 
@@ -460,7 +499,7 @@ static int launch_transform(int op, const nvtb_col_t* cols, int ncols, int64_t n
   int rc = check_cols(cols, ncols, n);
   if (rc) return rc;
   NVTB_REQUIRE(out != nullptr || ncols == 0, "out is NULL");
-  if (op != OP_FILL)
+  if (op != OP_FILL && op != OP_CLIP)
     NVTB_REQUIRE(out_dtype == NVTB_F32 || out_dtype == NVTB_F64,
                  "out_dtype must be float32 or float64");
   if (n == 0 || ncols == 0) return NVTB_OK;
@@ -475,8 +514,9 @@ static int launch_transform(int op, const nvtb_col_t* cols, int ncols, int64_t n
       cb.mask[c] = cols[c0 + c].validity;
       cb.dtype[c] = cols[c0 + c].dtype;
       cb.fill[c] = fill_vals ? fill_vals[c0 + c] : NAN;
-      cb.p0[c] = p0 ? p0[c0 + c] : 0.0;
-      cb.p1[c] = p1 ? p1[c0 + c] : 0.0;
+      const double none = (op == OP_CLIP || op == OP_CLIPLOG) ? NAN : 0.0;
+      cb.p0[c] = p0 ? p0[c0 + c] : none;
+      cb.p1[c] = p1 ? p1[c0 + c] : none;
       NVTB_REQUIRE(out[c0 + c] != nullptr, "out column is NULL");
       cb.out[c] = out[c0 + c];
       cb.filled[c] = filled ? filled[c0 + c] : nullptr;
@@ -484,6 +524,11 @@ static int launch_transform(int op, const nvtb_col_t* cols, int ncols, int64_t n
     dim3 g(grid, nc);
     if (op == OP_FILL) {
       fill_kernel<<<g, kThreads, 0, st>>>(cb, n);
+    } else if (op == OP_CLIP) {
+      clip_kernel<<<g, kThreads, 0, st>>>(cb, n);
+    } else if (op == OP_CLIPLOG) {
+      if (out_dtype == NVTB_F64) transform_kernel<OP_CLIPLOG, double><<<g, kThreads, 0, st>>>(cb, n);
+      else                        transform_kernel<OP_CLIPLOG, float><<<g, kThreads, 0, st>>>(cb, n);
     } else if (op == OP_NORMALIZE) {
       if (out_dtype == NVTB_F64) transform_kernel<OP_NORMALIZE, double><<<g, kThreads, 0, st>>>(cb, n);
       else                        transform_kernel<OP_NORMALIZE, float><<<g, kThreads, 0, st>>>(cb, n);
@@ -520,6 +565,14 @@ int nvtb_minmax_apply(const nvtb_col_t* cols, int ncols, int64_t n,
   NVTB_REQUIRE((mins && maxs) || ncols == 0, "mins/maxs NULL");
   return launch_transform(OP_MINMAX, cols, ncols, n, fill_vals, mins, maxs, out,
                           nullptr, out_dtype, stream);
+}
+
+int nvtb_cliplog_apply(const nvtb_col_t* cols, int ncols, int64_t n,
+                       const double* fill_vals, const double* min_vals,
+                       const double* max_vals, int take_log, void* const* out,
+                       int out_dtype, void* stream) {
+  return launch_transform(take_log ? OP_CLIPLOG : OP_CLIP, cols, ncols, n, fill_vals, min_vals, max_vals,
+                          out, nullptr, out_dtype, stream);
 }
 
 int nvtb_hash_bucket_apply(const nvtb_col_t* cols, int ncols, int64_t n,

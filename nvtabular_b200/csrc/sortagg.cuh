@@ -260,6 +260,9 @@ struct MergeSmem {
   uint16_t dx[kMergeTile + 2];       // exclusive prefix of "B key also in A"
 };
 
+// B_PACKED = false: B holds run heads (key << 32 | first index, sentinel at B[ub]) of a sorted
+// batch; true: B holds packed pairs (key << 32 | count) like A (cross-GPU shard merges)
+template <bool B_PACKED>
 static __global__ void __launch_bounds__(kRunThreads)
 merge_write_kernel(const uint64_t* __restrict__ A, const uint64_t* __restrict__ B,
                    const uint2* __restrict__ splits, const uint32_t* __restrict__ tile_off,
@@ -272,9 +275,10 @@ merge_write_kernel(const uint64_t* __restrict__ A, const uint64_t* __restrict__ 
   if (la + lb == 0) return;
   for (uint32_t i = threadIdx.x; i < la; i += kRunThreads) sm.a[i] = A[s0.x + i];
   for (uint32_t j = threadIdx.x; j < lb; j += kRunThreads) {
-    const uint64_t w = B[s0.y + j], w1 = B[s0.y + j + 1];      // B[ub] is the sentinel
+    const uint64_t w = B[s0.y + j];
     sm.bk[j] = pk_hi(w);
-    sm.bc[j] = pk_lo(w1) - pk_lo(w);
+    if (B_PACKED) sm.bc[j] = pk_lo(w);
+    else sm.bc[j] = pk_lo(B[s0.y + j + 1]) - pk_lo(w);           // B[ub] is the sentinel
   }
   __syncthreads();
   // B -> A: lower bounds and duplicate flags; blocked so that the prefix is in index order
@@ -384,6 +388,50 @@ table_to_pairs_kernel(Table t, uint64_t* __restrict__ out, unsigned long long* c
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const uint32_t y = __shfl_down_sync(0xFFFFFFFFu, mx, o); mx = y > mx ? y : mx; }
   if (lane == 0 && mx) atomicMax(max_count, (unsigned long long)mx);
+}
+
+// lower bound of every unsigned key bound[j] in the key-sorted packed pairs: out[j] = number of
+// pairs whose key is < bound[j] (one thread per bound)
+static __global__ void pairs_lower_bound_kernel(const uint64_t* __restrict__ pairs, int64_t n,
+                                                const uint32_t* __restrict__ bound, int m,
+                                                long long* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const uint32_t b = bound[j];
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    if (pk_hi(pairs[mid]) < b) lo = mid + 1; else hi = mid;
+  }
+  out[j] = (long long)lo;
+}
+
+// dst[seg_dst[s] + (i - seg_src[s])] = src[i] for i in [seg_src[s], seg_src[s + 1]): copies
+// nseg contiguous segments (seg_src ascending, seg_src[nseg] = n) to their destinations.  Used
+// to interleave the owners' count-ordered shards into the global (count desc, key asc) order:
+// a segment = the pairs of one count value on one owner.  4 elements per thread; the segment
+// of the first is found by binary search, the others usually share it.
+static __global__ void __launch_bounds__(kThreads)
+segment_copy_kernel(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst,
+                    const long long* __restrict__ seg_src, const long long* __restrict__ seg_dst,
+                    int nseg, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += stride) {
+    int lo = 0, hi = nseg;                       // last s with seg_src[s] <= i0
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (seg_src[mid] <= i0) lo = mid; else hi = mid;
+    }
+    int s = lo;
+    long long s_end = seg_src[s + 1], d0 = seg_dst[s], shift = d0 - seg_src[s];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t i = i0 + e;
+      if (i >= n) break;
+      while (i >= s_end) { ++s; s_end = seg_src[s + 1]; d0 = seg_dst[s]; shift = d0 - seg_src[s]; }
+      if (d0 >= 0) dst[i + shift] = src[i];          // seg_dst < 0: padding, skipped
+    }
+  }
 }
 
 }  // namespace nvtb

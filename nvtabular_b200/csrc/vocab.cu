@@ -1069,6 +1069,56 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* siz
 //                       columns this path exists for), then cut, meta sums and the lookup
 //                       build read the packed pairs directly
 //   hash table          exported into temporaries and handed to nvtb_vocab_build
+// tail shared by the packed-pair builds: `sorted` (owned by v from here on) holds n pairs
+// (key ^ 2^31) << 32 | count in (count desc, key asc) order
+static int finish_packed_vocab(nvtb_vocab* v, uint64_t* sorted, int64_t n, int64_t freq_threshold, int64_t max_size,
+                               int64_t num_buckets, cudaStream_t st) {
+  const int64_t oov_count = num_buckets > 0 ? num_buckets : 1;
+  v->packed = sorted;
+  // (2) cut + meta sums
+  int64_t n_keep = n;
+  VocabScalars* d_sc = nullptr;
+  NVTB_CUDA_OK(cudaMallocAsync(&d_sc, sizeof(VocabScalars), st));
+  const VocabScalars init = {n, 0, 0, 1, -1};
+  NVTB_CUDA_OK(cudaMemcpyAsync(d_sc, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+  const int g = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
+  if (freq_threshold > 0) {
+    NVTB_CUDA_OK(cudaMemsetAsync(&d_sc->n_keep, 0, sizeof(long long), st));
+    packed_count_ge_kernel<<<g, kThreads, 0, st>>>(sorted, n, freq_threshold, &d_sc->n_keep);
+    NVTB_LAUNCH_OK();
+    VocabScalars hs;
+    NVTB_CUDA_OK(cudaMemcpyAsync(&hs, d_sc, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    NVTB_CUDA_OK(cudaStreamSynchronize(st));
+    n_keep = hs.n_keep;
+  } else if (max_size > 0) {
+    n_keep = std::min<int64_t>(n, max_size - (oov_count + 2));
+    NVTB_CUDA_OK(cudaMemcpyAsync(&d_sc->n_keep, &n_keep, sizeof(long long), cudaMemcpyHostToDevice, st));
+    NVTB_CUDA_OK(cudaStreamSynchronize(st));      // n_keep is a host temporary
+  }
+  packed_scalars_kernel<<<g, kThreads, 0, st>>>(sorted, n, n_keep, d_sc);
+  NVTB_LAUNCH_OK();
+  v->info.n_kept = n_keep;
+  // (3) narrow lookup of the kept keys
+  v->t.capacity = pow2_at_least(2 * n_keep);
+  v->t.min_key_pos = -1;
+  v->t.narrow = 1;
+  NVTB_CUDA_OK(cudaMallocAsync(&v->t.slots, sizeof(int64_t) * v->t.capacity, st));
+  NVTB_CUDA_OK(cudaMemsetAsync(v->t.slots, 0, sizeof(int64_t) * v->t.capacity, st));
+  if (n_keep > 0) {
+    const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>((n_keep + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
+    lookup_build_packed_kernel<<<g1, kThreads, 0, st>>>(sorted, n_keep, reinterpret_cast<unsigned long long*>(v->t.slots),
+                                                        v->t.capacity);
+    NVTB_LAUNCH_OK();
+    if (n_keep <= kEncSmemMaxKeys) {        // the shared-memory encode reads int64 keys
+      NVTB_CUDA_OK(cudaMallocAsync(&v->keys, sizeof(int64_t) * n_keep, st));
+      packed_unpack_kernel<<<g1, kThreads, 0, st>>>(sorted, n_keep, v->keys, nullptr);
+      NVTB_LAUNCH_OK();
+    }
+  }
+  v->d_sc = d_sc;
+  return vocab_post(v, st);
+}
+
 int nvtb_vocab_build_from_hashagg(nvtb_vocab_t** out, nvtb_hashagg_t* h, int64_t freq_threshold,
                                   int64_t max_size, int64_t num_buckets, int key_bits,
                                   int64_t size_bound, void* stream) {
@@ -1139,49 +1189,34 @@ int nvtb_vocab_build_from_hashagg(nvtb_vocab_t** out, nvtb_hashagg_t* h, int64_t
     if (sorted == p0) { if (p1) NVTB_CUDA_OK(cudaFreeAsync(p1, st)); }
     else NVTB_CUDA_OK(cudaFreeAsync(p0, st));
   }
-  v->packed = sorted;
-  // (2) cut + meta sums
-  int64_t n_keep = n;
-  VocabScalars* d_sc = nullptr;
-  NVTB_CUDA_OK(cudaMallocAsync(&d_sc, sizeof(VocabScalars), st));
-  const VocabScalars init = {n, 0, 0, 1, -1};
-  NVTB_CUDA_OK(cudaMemcpyAsync(d_sc, &init, sizeof(init), cudaMemcpyHostToDevice, st));
-  const int g = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
-  if (freq_threshold > 0) {
-    NVTB_CUDA_OK(cudaMemsetAsync(&d_sc->n_keep, 0, sizeof(long long), st));
-    packed_count_ge_kernel<<<g, kThreads, 0, st>>>(sorted, n, freq_threshold, &d_sc->n_keep);
-    NVTB_LAUNCH_OK();
-    VocabScalars hs;
-    NVTB_CUDA_OK(cudaMemcpyAsync(&hs, d_sc, sizeof(hs), cudaMemcpyDeviceToHost, st));
-    NVTB_CUDA_OK(cudaStreamSynchronize(st));
-    n_keep = hs.n_keep;
-  } else if (max_size > 0) {
-    n_keep = std::min<int64_t>(n, max_size - (oov_count + 2));
-    NVTB_CUDA_OK(cudaMemcpyAsync(&d_sc->n_keep, &n_keep, sizeof(long long), cudaMemcpyHostToDevice, st));
-    NVTB_CUDA_OK(cudaStreamSynchronize(st));      // n_keep is a host temporary
-  }
-  packed_scalars_kernel<<<g, kThreads, 0, st>>>(sorted, n, n_keep, d_sc);
-  NVTB_LAUNCH_OK();
-  v->info.n_kept = n_keep;
-  // (3) narrow lookup of the kept keys
-  v->t.capacity = pow2_at_least(2 * n_keep);
-  v->t.min_key_pos = -1;
-  v->t.narrow = 1;
-  NVTB_CUDA_OK(cudaMallocAsync(&v->t.slots, sizeof(int64_t) * v->t.capacity, st));
-  NVTB_CUDA_OK(cudaMemsetAsync(v->t.slots, 0, sizeof(int64_t) * v->t.capacity, st));
-  if (n_keep > 0) {
-    const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>((n_keep + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
-    lookup_build_packed_kernel<<<g1, kThreads, 0, st>>>(sorted, n_keep, reinterpret_cast<unsigned long long*>(v->t.slots),
-                                                        v->t.capacity);
-    NVTB_LAUNCH_OK();
-    if (n_keep <= kEncSmemMaxKeys) {        // the shared-memory encode reads int64 keys
-      NVTB_CUDA_OK(cudaMallocAsync(&v->keys, sizeof(int64_t) * n_keep, st));
-      packed_unpack_kernel<<<g1, kThreads, 0, st>>>(sorted, n_keep, v->keys, nullptr);
-      NVTB_LAUNCH_OK();
-    }
-  }
-  v->d_sc = d_sc;
-  rc = vocab_post(v, st);
+  rc = finish_packed_vocab(v, sorted, n, freq_threshold, max_size, num_buckets, st);
+  if (rc) { nvtb_vocab_destroy(v); return rc; }
+  *out = v;
+  return NVTB_OK;
+}
+
+// Vocabulary from packed pairs that are ALREADY in (count desc, key asc) order — the cross-GPU
+// merge (nvtabular_b200/dist.py) assembles that order from the owners' shards.  The array is
+// copied; cut, meta sums and the lookup table are the single-GPU code.
+int nvtb_vocab_build_from_pairs(nvtb_vocab_t** out, const uint64_t* ordered_pairs, int64_t n, int64_t null_size,
+                                int64_t freq_threshold, int64_t max_size, int64_t num_buckets, void* stream) {
+  NVTB_REQUIRE(out != nullptr && n >= 0 && n < (int64_t)0x7FFFFFF0, "NULL out or n out of range");
+  NVTB_REQUIRE(n == 0 || ordered_pairs != nullptr, "NULL pairs");
+  ensure_pool_configured();
+  NVTB_REQUIRE(!(freq_threshold > 0 && max_size > 0), "cannot use freq_threshold together with max_size");
+  const int64_t oov_count = num_buckets > 0 ? num_buckets : 1;
+  NVTB_REQUIRE(!(max_size > 0 && max_size < oov_count + 2),
+               "`max_size` can never be less than the maximum of `num_buckets + 2` and `3`");
+  cudaStream_t st = (cudaStream_t)stream;
+  nvtb_vocab* v = new (std::nothrow) nvtb_vocab();
+  NVTB_REQUIRE(v != nullptr, "host allocation failed");
+  memset(v, 0, sizeof(*v));
+  v->info.n_total = n;
+  v->info.null_size = null_size;
+  uint64_t* p0 = nullptr;
+  NVTB_CUDA_OK(cudaMallocAsync(&p0, sizeof(uint64_t) * (n > 0 ? n : 1), st));
+  if (n > 0) NVTB_CUDA_OK(cudaMemcpyAsync(p0, ordered_pairs, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, st));
+  int rc = finish_packed_vocab(v, p0, n, freq_threshold, max_size, num_buckets, st);
   if (rc) { nvtb_vocab_destroy(v); return rc; }
   *out = v;
   return NVTB_OK;

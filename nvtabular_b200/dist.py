@@ -261,3 +261,166 @@ def global_merge_many(aggs, engine=None, owner_pool=None):
             f"{marks[i][0]} {1e3 * (marks[i][1] - marks[i - 1][1]):.2f} ms" for i in range(1, len(marks)))
               + f"; keys sent {sk.numel()}, owned {sum(t.numel() for t in owned_k)}", flush=True)
     return out
+
+
+# =======================================================================================
+# High-cardinality columns: key-RANGE exchange of sorted packed pairs
+# =======================================================================================
+def global_merge_sorted(aggs, engine=None):
+    """Cross-GPU merge of int32 key-count columns held as SORTED accumulators (key-ordered packed
+    pairs word = (key ^ 2^31) << 32 | count; csrc/sortagg.cuh).  Returns, per column,
+    (ordered_pairs, null_size): the GLOBAL vocabulary in (count desc, key asc) order, identical
+    on every rank, ready for engine.Vocab.build_from_pairs.
+
+    Nothing O(U_global) is sorted twice and nothing is re-hashed:
+      1. owners are key RANGES; the split points are the mean of the ranks' local quantiles, so
+         the local accumulator — already key-ordered — is already grouped by owner: the send
+         buffer IS the accumulator, W-1 binary searches give the split sizes
+      2. ONE all-to-all of 8-byte pairs; every owner receives W key-sorted runs and merges them
+         pairwise adding counts (log2 W streaming merge rounds, nvtb_pairs_merge)
+      3. every owner orders ITS shard by count (stable radix on the count bits in use) and
+         run-length encodes the counts: a table of (count value, #keys) — a few thousand rows
+      4. the tables are all-gathered; because owners hold disjoint, increasing key ranges, the
+         global position of owner r's group of count c is
+             #keys with a larger count (all owners) + #keys with count c on owners < r,
+         computed identically on every rank from the small tables
+      5. the count-ordered shards are all-gathered (8 B per distinct key — the "encode-table
+         broadcast" of SURVEY.md 8e) and copied group by group to those positions
+         (nvtb_segment_copy_u64): a streaming pass, no global sort.
+    Reference analogue: the split_out shuffle + per-bucket concat/groupby + sort + shared
+    filesystem read of nvtabular/ops/categorify.py:1036-1049, 1054-1070, 1296-1337, 1627-1643."""
+    if engine is None:
+        from . import engine
+    import os
+    import time
+    import torch.distributed as dist
+    w, rank = world()
+    trace = bool(os.environ.get("NVTB_TRACE")) and w > 1
+    out = []
+    if not aggs:
+        return out
+    dev = torch.device("cuda", torch.cuda.current_device())
+    sizes = [a.size() for a in aggs]                      # (n_unique, null_size) per column
+    ns = torch.tensor([s[1] for s in sizes], dtype=torch.int64, device=dev)
+    if w > 1:
+        dist.all_reduce(ns, op=dist.ReduceOp.SUM)
+    ns_h = [int(x) for x in ns.cpu().tolist()]
+    for c, agg in enumerate(aggs):
+        t0 = time.perf_counter()
+        p = agg.export_packed(dev)
+        n = p.numel()
+        if w == 1:
+            S = p
+        else:
+            # 1. splitters from the ranks' local quantiles
+            q = torch.zeros(w, dtype=torch.int64, device=dev)          # [n, q_1 .. q_{w-1}]
+            q[0] = n
+            if n:
+                idx = (torch.arange(1, w, device=dev, dtype=torch.int64) * n) // w
+                q[1:] = (p[idx] >> 32) & 0xFFFFFFFF
+            allq = torch.empty(w * w, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allq, q)
+            allq = allq.view(w, w)
+            live = (allq[:, 0] > 0).to(torch.float64)
+            nlive = live.sum().clamp(min=1.0)
+            spl = torch.floor((allq[:, 1:].to(torch.float64) * live[:, None]).sum(dim=0) / nlive).to(torch.int64)
+            lb = engine.pairs_lower_bounds(p, spl) if n else torch.zeros(w - 1, dtype=torch.int64, device=dev)
+            edges = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), lb,
+                               torch.full((1,), n, dtype=torch.int64, device=dev)])
+            send_counts = edges[1:] - edges[:-1]
+            recv_counts = torch.empty_like(send_counts)
+            dist.all_to_all_single(recv_counts, send_counts)
+            sc_h = [int(x) for x in send_counts.cpu().tolist()]
+            rc_h = [int(x) for x in recv_counts.cpu().tolist()]
+            # 2. one all-to-all of packed pairs, then the owner's pairwise merges
+            recv = torch.empty(sum(rc_h), dtype=torch.int64, device=dev)
+            dist.all_to_all_single(recv, p, output_split_sizes=rc_h, input_split_sizes=sc_h)
+            del p
+            runs, off = [], 0
+            for r in range(w):
+                runs.append(recv[off: off + rc_h[r]])
+                off += rc_h[r]
+            while len(runs) > 1:
+                nxt = []
+                for i in range(0, len(runs) - 1, 2):
+                    nxt.append(engine.pairs_merge(runs[i], runs[i + 1]))
+                if len(runs) & 1:
+                    nxt.append(runs[-1])
+                runs = nxt
+            S = runs[0]
+            del recv, runs
+        t1 = time.perf_counter()
+        # 3. owner-side order by count (desc), stable => key asc within a count
+        n_s = S.numel()
+        if n_s:
+            cnt = S & 0xFFFFFFFF
+            mx = int(cnt.max().item())
+            bits = max(1, mx.bit_length())
+            C = engine.radix_sort(S, 0, bits, descending=True) if bits > 1 or mx > 1 else S
+            if C is not S:
+                cnt = C & 0xFFFFFFFF
+            vals, lens = torch.unique_consecutive(cnt, return_counts=True)
+            del cnt
+        else:
+            C = S
+            vals = torch.zeros(0, dtype=torch.int64, device=dev)
+            lens = torch.zeros(0, dtype=torch.int64, device=dev)
+        del S
+        if w == 1:
+            out.append((C, ns_h[c]))
+            continue
+        # 4. small tables -> destination of every (owner, count value) group
+        meta = torch.tensor([vals.numel(), n_s], dtype=torch.int64, device=dev)
+        allmeta = torch.empty(2 * w, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allmeta, meta)
+        allmeta_h = allmeta.view(w, 2).cpu()
+        d_all = [int(x) for x in allmeta_h[:, 0].tolist()]
+        n_all = [int(x) for x in allmeta_h[:, 1].tolist()]
+        d_max, n_max, n_glob = max(max(d_all), 1), max(max(n_all), 1), sum(n_all)
+        tab = torch.zeros(2 * d_max, dtype=torch.int64, device=dev)
+        tab[: vals.numel()] = vals
+        tab[d_max: d_max + lens.numel()] = lens
+        alltab = torch.empty(w * 2 * d_max, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(alltab, tab)
+        alltab = alltab.view(w, 2, d_max)
+        g_val, g_len, g_src, pad_src = [], [], [], []
+        for r in range(w):                                  # groups listed owner-major
+            g_val.append(alltab[r, 0, : d_all[r]])
+            ln = alltab[r, 1, : d_all[r]]
+            g_len.append(ln)
+            g_src.append(r * n_max + torch.cumsum(ln, 0) - ln)
+        g_val, g_len, g_src = torch.cat(g_val), torch.cat(g_len), torch.cat(g_src)
+        order = torch.sort(g_val, descending=True, stable=True).indices     # ties keep owner order
+        dst_sorted = torch.cumsum(g_len[order], 0) - g_len[order]
+        g_dst = torch.empty_like(dst_sorted)
+        g_dst[order] = dst_sorted
+        # padding between the owners' shards in the gathered buffer: segments that are skipped
+        seg_src = [g_src]
+        seg_dst = [g_dst]
+        for r in range(w):
+            if n_all[r] < n_max:
+                seg_src.append(torch.tensor([r * n_max + n_all[r]], dtype=torch.int64, device=dev))
+                seg_dst.append(torch.tensor([-1], dtype=torch.int64, device=dev))
+        seg_src, seg_dst = torch.cat(seg_src), torch.cat(seg_dst)
+        o2 = torch.sort(seg_src).indices
+        seg_src = torch.cat([seg_src[o2], torch.tensor([w * n_max], dtype=torch.int64, device=dev)])
+        seg_dst = seg_dst[o2].contiguous()
+        # 5. all-gather the count-ordered shards, interleave them group by group
+        padded = torch.zeros(n_max, dtype=torch.int64, device=dev)
+        padded[:n_s] = C
+        del C
+        gathered = torch.empty(w * n_max, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, padded)
+        del padded
+        ordered = torch.empty(n_glob, dtype=torch.int64, device=dev)
+        if n_glob:
+            engine.segment_copy(gathered, ordered, seg_src, seg_dst)
+        del gathered
+        out.append((ordered, ns_h[c]))
+        if trace and rank == 0:
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            print(f"[nvtb trace] merge_sorted col {c}: local {n} pairs, shard {n_s}, global {n_glob}; "
+                  f"exchange+merge {1e3 * (t1 - t0):.2f} ms, order+gather+interleave {1e3 * (t2 - t1):.2f} ms",
+                  flush=True)
+    return out

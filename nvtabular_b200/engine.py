@@ -186,6 +186,24 @@ def minmax_apply(cols: Sequence[Column], mins, maxs, out_dtype=np.float64):
     return [Column(o, None if c.fill is not None else c.validity, c.offsets) for o, c in zip(outs, cols)]
 
 
+def cliplog_apply(cols: Sequence[Column], min_value=None, max_value=None, take_log=False, out_dtype=np.float32):
+    """Clip (+ LogOp) with an upstream FillMissing fused in (nvtb_cliplog_apply).  take_log=False
+    keeps every column's dtype; nulls that are not filled stay nulls."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    n = _check_same_len(cols)
+    code = dtype_code(out_dtype) if take_log else 0
+    outs = _alloc_like(cols, _CODE2TORCH[code]) if take_log else [torch.empty_like(c.data) for c in cols]
+    lo = _lib.double_array([NAN if min_value is None else float(min_value)] * len(cols))
+    hi = _lib.double_array([NAN if max_value is None else float(max_value)] * len(cols))
+    with _timed("cliplog", _in_bytes(cols) + sum(o.numel() * o.element_size() for o in outs)):
+        _lib.check(lib.nvtb_cliplog_apply(_descs(cols), len(cols), n, _fills(cols), lo, hi, 1 if take_log else 0,
+                                          _lib.ptr_array([o.data_ptr() for o in outs]), code, _lib.stream_ptr()))
+    _count()
+    return [Column(o, None if c.fill is not None else c.validity, c.offsets, None, None, c.is_bool and not take_log)
+            for o, c in zip(outs, cols)]
+
+
 def hash_bucket(cols: Sequence[Column], num_buckets: int, add: int = 0, out_dtype=np.int32) -> torch.Tensor:
     """hash(cols...) % num_buckets + add (nvtb_hash_bucket_apply)."""
     _lib.require_cuda()
@@ -263,6 +281,21 @@ class HashAgg:
         m = c_int(0)
         _lib.check(self.lib.nvtb_hashagg_mode(self.h, byref(m)))
         return m.value
+
+    def to_sorted(self):
+        """make the handle a sorted accumulator (key-ordered packed pairs), see csrc/sortagg.cuh"""
+        _lib.check(self.lib.nvtb_hashagg_to_sorted(self.h, _lib.stream_ptr()))
+        _count(3)
+
+    def export_packed(self, device="cuda") -> torch.Tensor:
+        """packed pairs (key ^ 2^31) << 32 | count of a sorted accumulator, key order, as the bit
+        pattern of an int64 tensor"""
+        n = c_int64(0)
+        _lib.check(self.lib.nvtb_hashagg_export_packed(self.h, None, byref(n), _lib.stream_ptr()))
+        out = torch.empty(n.value, dtype=torch.int64, device=device)
+        if n.value:
+            _lib.check(self.lib.nvtb_hashagg_export_packed(self.h, _ptr(out), byref(n), _lib.stream_ptr()))
+        return out
 
     def insert(self, key: Column, agg_cols: Sequence[Column] = ()):
         n = key.data.numel()
@@ -401,6 +434,19 @@ class Vocab:
         return cls(h, lib)
 
     @classmethod
+    def build_from_pairs(cls, ordered_pairs: torch.Tensor, null_size=0, freq_threshold=0, max_size=0, num_buckets=0):
+        """vocabulary from packed pairs already in (count desc, key asc) order (cross-GPU merge)"""
+        _lib.require_cuda()
+        lib = _lib.load()
+        h = c_void_p()
+        with _timed("vocab_build", float(ordered_pairs.numel() * 16)):
+            _lib.check(lib.nvtb_vocab_build_from_pairs(byref(h), _ptr(ordered_pairs), ordered_pairs.numel(),
+                                                       int(null_size), int(freq_threshold or 0), int(max_size or 0),
+                                                       int(num_buckets or 0), _lib.stream_ptr()))
+        _count(4)
+        return cls(h, lib, n_total=ordered_pairs.numel())
+
+    @classmethod
     def from_arrays(cls, keys: torch.Tensor, sizes: Optional[torch.Tensor] = None):
         _lib.require_cuda()
         lib = _lib.load()
@@ -435,6 +481,39 @@ class Vocab:
                 _ptr(out), code, _lib.stream_ptr()))
         _count()
         return out
+
+
+def pairs_lower_bounds(pairs: torch.Tensor, bounds: torch.Tensor) -> torch.Tensor:
+    """number of key-sorted packed pairs whose unsigned key is below each of `bounds` (int64
+    tensor of values in [0, 2^32]; 2^32 = "everything") -> int64 tensor on the device"""
+    lib = _lib.load()
+    n = pairs.numel()
+    full = bounds >= (1 << 32)
+    b = torch.where(full, torch.zeros_like(bounds), bounds)
+    b32 = torch.where(b >= (1 << 31), b - (1 << 32), b).to(torch.int32).contiguous()
+    out = torch.empty(bounds.numel(), dtype=torch.int64, device=pairs.device)
+    _lib.check(lib.nvtb_pairs_lower_bounds(_ptr(pairs), n, _ptr(b32), b32.numel(), _ptr(out), _lib.stream_ptr()))
+    _count()
+    return torch.where(full, torch.full_like(out, n), out)
+
+
+def pairs_merge(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """merge of two key-sorted, key-unique packed-pair arrays, counts of equal keys added"""
+    lib = _lib.load()
+    out = torch.empty(a.numel() + b.numel(), dtype=torch.int64, device=a.device)
+    n = c_int64(0)
+    _lib.check(lib.nvtb_pairs_merge(_ptr(a), a.numel(), _ptr(b), b.numel(), _ptr(out), byref(n), _lib.stream_ptr()))
+    _count(4)
+    return out[: n.value]
+
+
+def segment_copy(src: torch.Tensor, dst: torch.Tensor, seg_src: torch.Tensor, seg_dst: torch.Tensor):
+    """dst[seg_dst[s] + k] = src[seg_src[s] + k] for every segment s (seg_src: nseg + 1 ascending
+    offsets ending at src.numel(); seg_dst < 0 skips a segment)"""
+    lib = _lib.load()
+    _lib.check(lib.nvtb_segment_copy_u64(_ptr(src), _ptr(dst), _ptr(seg_src), _ptr(seg_dst), seg_dst.numel(),
+                                         src.numel(), _lib.stream_ptr()))
+    _count()
 
 
 def radix_sort(data: torch.Tensor, lo_bit: int = 0, hi_bit: Optional[int] = None, descending=False) -> torch.Tensor:

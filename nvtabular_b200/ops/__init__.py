@@ -2,6 +2,7 @@
 (reference nvtabular/ops/__init__.py:21-54; scope per SURVEY.md §8)."""
 from .base import Operator, StatOperator  # noqa: F401
 from .categorify import Categorify  # noqa: F401
+from .clip_log import Clip, LogOp  # noqa: F401
 from .fill import FillMissing  # noqa: F401
 from .hash_bucket import HashBucket, emb_sz_rule  # noqa: F401
 from .join_groupby import JoinGroupby  # noqa: F401

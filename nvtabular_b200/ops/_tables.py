@@ -1,0 +1,45 @@
+"""Host frame <-> device key helpers shared by the operators that keep their fitted state in
+parquet files (reference layout: unique.<col>.parquet / cat_stats.<name>.parquet,
+nvtabular/ops/categorify.py:719-822, 1073-1137): a workflow reloaded from disk rebuilds its
+device tables from those files."""
+from typing import List, Tuple
+
+import numpy as np
+import pandas as pd
+import torch
+
+from ..column import DeviceFrame, unpack_validity
+from .keyspace import ComboKeySpace, KeySpace, _leaf
+
+
+def keys_from_frame(df: pd.DataFrame, key_names: List[str]) -> Tuple[object, torch.Tensor, torch.Tensor]:
+    """-> (key space, int64 device keys [n], bool device mask [n] of rows whose key is null).
+    The key space is rebuilt from the values present in the file (unseen values are
+    out-of-vocabulary by construction)."""
+    frame = DeviceFrame.from_pandas(df[key_names].reset_index(drop=True))
+    cols = [_leaf(frame[n]) for n in key_names]
+    n = len(df)
+    if len(key_names) > 1:
+        space = ComboKeySpace.fit([cols], ncomp=len(key_names))
+        key = space.keys_for(cols)
+    else:
+        space = KeySpace.for_columns(cols)
+        key = space.keys_for(cols[0])
+    data = key.data.to(torch.int64)
+    if key.validity is not None:
+        isnull = ~unpack_validity(key.validity, n)
+    else:
+        isnull = torch.zeros(n, dtype=torch.bool, device=data.device)
+    return space, data, isnull
+
+
+def key_columns(space, key_names: List[str], keys: np.ndarray, with_null_row: bool = False) -> dict:
+    """decoded key columns of a table ({name: Series}); `with_null_row` appends the null group"""
+    comps = space.decode(keys) if isinstance(space, ComboKeySpace) else [space.decode(keys)]
+    out = {}
+    for name, v in zip(key_names, comps):
+        v = pd.Series(v, dtype=object if getattr(v, "dtype", None) == object else None)
+        if with_null_row:
+            v = pd.concat([v.astype(object), pd.Series([None], dtype=object)], ignore_index=True)
+        out[name] = v
+    return out

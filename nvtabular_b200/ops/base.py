@@ -50,6 +50,33 @@ class Operator(metaclass=_OperatorMeta):
     def __rrshift__(self, other):
         return ColumnSelector(other) >> self
 
+    # ------------------------------------------------ serving hooks (reference operator contract)
+    def inference_initialize(self, col_selector, inference_config):
+        """an inference-time replacement of this op for dict-of-arrays requests, or None
+        (merlin.dag BaseOperator hook; overridden by Categorify / FillMissing)"""
+        return None
+
+    def compute_selector(self, input_schema, selector, parents_selector=None, dependencies_selector=None):
+        """the columns this op reads: its parents' outputs (reference categorify.py:589-597)"""
+        sel = parents_selector if parents_selector is not None else selector
+        missing = [n for n in sel.names if input_schema is not None and n not in input_schema]
+        if missing:
+            raise ValueError(f"Missing columns {missing} found in operator {type(self).__name__} "
+                             "during computing input selector.")
+        return sel
+
+    @property
+    def supports(self):
+        from ..inference import Supports
+        return Supports.GPU_DATAFRAME | Supports.CPU_DATAFRAME
+
+    @property
+    def supported_formats(self):
+        """frames in, frames out by default; ops with a dict-of-arrays path add the *_DICT_ARRAY bits
+        (reference nvtabular/ops/normalize.py:92-108)"""
+        from ..inference import DataFormats
+        return DataFormats.PANDAS_DATAFRAME | DataFormats.CUDF_DATAFRAME
+
     # -------------------------------------------------------------------- schema
     def _compute_dtype(self, col_schema: ColumnSchema, input_schema: Schema) -> ColumnSchema:
         dtype = col_schema.dtype

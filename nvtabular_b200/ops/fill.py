@@ -67,6 +67,13 @@ class FillMissing(Operator):
             df[n] = Column(c.data, c.validity, c.offsets, c.dictionary, self.fill_val, c.is_bool)
         return df
 
+    def inference_initialize(self, col_selector, inference_config):
+        """fill.py:59-65: the host dict-of-arrays transform for serving"""
+        if self.add_binary_cols:
+            return None
+        from ..inference import FillTransform
+        return FillTransform(self)
+
     def column_mapping(self, col_selector):
         mapping = super().column_mapping(col_selector)
         if self.add_binary_cols:

@@ -41,6 +41,30 @@ class GroupTable:
         self.handle = engine.GroupStats(keys, stats, null_row)
         self.path = None
 
+    @classmethod
+    def from_parquet(cls, name, path, sep="_") -> "GroupTable":
+        """rebuild the device table from a cat_stats.<name>.parquet file (this engine's or the
+        reference's, categorify.py:1073-1137): key columns = everything that is not a
+        `<name>_...` statistic; the row with a null key becomes the null group"""
+        from ._tables import keys_from_frame
+        df = pd.read_parquet(path)
+        stat_names = [c for c in df.columns if c.startswith(name + sep)]
+        key_names = [c for c in df.columns if c not in stat_names]
+        space, keys, isnull = keys_from_frame(df, key_names)
+        mat = torch.from_numpy(df[stat_names].to_numpy(dtype=np.float64)).to(keys.device) if stat_names else \
+            torch.zeros((len(df), 1), dtype=torch.float64, device=keys.device)
+        null_idx = torch.nonzero(isnull).flatten()
+        keep = ~isnull
+        null_row = -1
+        stats = mat[keep]
+        if null_idx.numel():
+            stats = torch.cat([stats, mat[null_idx[:1]]], dim=0)
+            null_row = int(keep.sum().item())
+        t = cls(name, key_names, space, keys[keep].contiguous(), stat_names, stats.contiguous(), null_row, None)
+        t.f32_stats = {c for c in stat_names if df[c].dtype == np.float32 and c.rsplit(sep, 1)[-1] in ("sum", "min", "max")}
+        t.path = path
+        return t
+
     def frame(self) -> pd.DataFrame:
         k = self.keys.cpu().numpy()
         if isinstance(self.space, ComboKeySpace):
@@ -56,8 +80,14 @@ class GroupTable:
                 v = pd.concat([v, pd.Series([None], dtype=object)], ignore_index=True)
             data[name] = v
         rows = n + (1 if self.null_row >= 0 else 0)
+        f32 = getattr(self, "f32_stats", ())
         for j, sn in enumerate(self.stat_names):
-            data[sn] = st[:rows, j]
+            col = st[:rows, j]
+            if sn.endswith("_count"):                  # the reference's file holds integer counts
+                col = col.astype(np.int64)
+            elif sn in f32:                            # ... and float32 sums of float32 columns
+                col = col.astype(np.float32)
+            data[sn] = col
         return pd.DataFrame(data)
 
     def write(self, base):
@@ -178,14 +208,14 @@ class JoinGroupby(StatOperator):
         for name, names in self._groups(col_selector):
             if not all(n in df for n in names):
                 continue
-            t = self.tables[name]
+            t = self._table(name)
             key = t.space.keys_for([df[n] for n in names]) if isinstance(t.space, ComboKeySpace) \
                 else t.space.keys_for(df[names[0]])
             idx, dts, out_names = [], [], []
             for j, sn in enumerate(t.stat_names):
                 if sn in new_df:
                     continue
-                dt = np.float64
+                dt = np.float32 if sn in getattr(t, "f32_stats", ()) else np.float64
                 for agg, d in AGG_DTYPES.items():
                     if sn.endswith(f"{self.name_sep}{agg}"):
                         dt = d
@@ -196,6 +226,15 @@ class JoinGroupby(StatOperator):
             for sn, o in zip(out_names, outs):
                 new_df[sn] = Column(o)
         return new_df
+
+    def _table(self, name) -> GroupTable:
+        t = self.tables.get(name)
+        if t is None:                       # a workflow reloaded from disk: read the stat file
+            path = self.categories.get(self.storage_name.get(name, name))
+            if path is None:
+                raise KeyError(name)
+            t = self.tables[name] = GroupTable.from_parquet(name, path, self.name_sep)
+        return t
 
     def column_mapping(self, col_selector):
         column_mapping = {}
@@ -247,4 +286,10 @@ def fit_group_table(name, names, parts, cont, stats, sep="_") -> GroupTable:
     for df in parts:
         key = space.keys_for([df[n] for n in names]) if len(names) > 1 else space.keys_for(df[names[0]])
         agg.insert(key, [_leaf(df[c]) for c in cont])
-    return build_group_table(name, names, space, agg, cont, stats, sep)
+    t = build_group_table(name, names, space, agg, cont, stats, sep)
+    # pandas / cuDF keep sum, min and max of a float32 column in float32 (the stat file of
+    # the reference holds that dtype, join_groupby.py:200-215 reads it back unchanged)
+    import torch as _torch
+    t.f32_stats = {_make_name(name, c, a, sep=sep) for c in cont for a in ("sum", "min", "max")
+                   if parts and _leaf(parts[0][c]).data.dtype == _torch.float32}
+    return t

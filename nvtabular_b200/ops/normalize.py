@@ -49,6 +49,17 @@ class _MomentsOp(StatOperator):
     def output_dtype(self):
         return self.out_dtype or np.float64
 
+    @property
+    def supports(self):
+        from ..inference import Supports
+        return Supports.CPU_DICT_ARRAY | Supports.GPU_DICT_ARRAY | Supports.CPU_DATAFRAME | Supports.GPU_DATAFRAME
+
+    @property
+    def supported_formats(self):          # normalize.py:100-108
+        from ..inference import DataFormats
+        return (DataFormats.PANDAS_DATAFRAME | DataFormats.CUDF_DATAFRAME | DataFormats.NUMPY_DICT_ARRAY
+                | DataFormats.CUPY_DICT_ARRAY)
+
 
 class Normalize(_MomentsOp):
     """(x - mean) / std with ddof=1 statistics (normalize.py:61-90)."""

@@ -154,26 +154,111 @@ class TargetEncoding(StatOperator):
         if means is not None:
             for t, m in zip(self.target_columns, means):
                 self.means[t] = float(m)
+        for name, g in groups.items():
+            self._finalize_group(name, g)
+
+    def _finalize_group(self, name, g: _TEGroup):
+        """pre-combine the TE value of every (fold, group) — target_encoding.py:341-349, 360-363"""
         y_mean = self.target_mean or self.means
         targets = self.target_columns
         p = float(self.p_smooth)
-        ym = torch.tensor([float(y_mean[t]) for t in targets], dtype=torch.float64, device="cuda")
-        for name, g in groups.items():
-            keys, count_all, sum_all = g._all
-            if self.kfold > 1:
-                fk, count_f, sum_f = g._fold
-                a, gid = engine.unpack_keys2(fk.cpu().numpy())
-                gid_t = torch.from_numpy(gid.astype(np.int64)).to(fk.device)
-                # target_encoding.py:341-349
-                te = (sum_all[gid_t] - sum_f + p * ym) / ((count_all[gid_t] - count_f)[:, None] + p)
-                g.handle = engine.GroupStats(fk, te, -1)
-                g.fold_keys = (a, gid)
-                self.stats[_make_name(self.fold_name, *g.names, sep=self.name_sep)] = name
-            else:
-                te = (sum_all + p * ym) / (count_all[:, None] + p)       # :360-363
-                g.handle = engine.GroupStats(keys, te, g.n_groups)
-            self.stats[name] = name
-            self._groups[name] = g
+        keys, count_all, sum_all = g._all
+        ym = torch.tensor([float(y_mean[t]) for t in targets], dtype=torch.float64, device=keys.device)
+        if self.kfold > 1:
+            fk, count_f, sum_f = g._fold
+            a, gid = engine.unpack_keys2(fk.cpu().numpy())
+            gid_t = torch.from_numpy(gid.astype(np.int64)).to(fk.device)
+            te = (sum_all[gid_t] - sum_f + p * ym) / ((count_all[gid_t] - count_f)[:, None] + p)
+            g.handle = engine.GroupStats(fk, te, -1)
+            g.fold_keys = (a, gid)
+            self.stats.setdefault(_make_name(self.fold_name, *g.names, sep=self.name_sep), name)
+        else:
+            te = (sum_all + p * ym) / (count_all[:, None] + p)
+            g.handle = engine.GroupStats(keys, te, g.n_groups)
+        self.stats.setdefault(name, name)
+        self._groups[name] = g
+
+    # ------------------------------------------------------------- artefacts (cat_stats files)
+    def _write_group(self, name, g: _TEGroup, base):
+        """cat_stats.<name>.parquet (+ cat_stats.__fold___<name>.parquet): group keys, count and
+        per-target sums — the reference's TargetEncoding state (target_encoding.py:190-214 via
+        categorify.py:1543-1555), enough to rebuild the op after Workflow.load"""
+        import pandas as pd
+        from ._tables import key_columns
+        os.makedirs(base, exist_ok=True)
+        targets = self.target_columns
+        keys, count_all, sum_all = g._all
+        k = keys.cpu().numpy()
+        data = key_columns(g.space, g.names, k, with_null_row=True)
+        data[f"{name}_count"] = count_all.cpu().numpy().astype(np.int64)
+        sa = sum_all.cpu().numpy()
+        for j, t in enumerate(targets):
+            data[f"{name}_{t}_sum"] = sa[:, j]
+        path = os.path.join(base, f"cat_stats.{name}.parquet")
+        pd.DataFrame(data).to_parquet(path)
+        self.stats[name] = path
+        if self.kfold > 1:
+            fname = _make_name(self.fold_name, *g.names, sep=self.name_sep)
+            fk, count_f, sum_f = g._fold
+            a, gid = g.fold_keys
+            kk = np.concatenate([k, np.zeros(1, dtype=k.dtype)])        # row U = the null group
+            fdata = {self.fold_name: a.astype(np.int64)}
+            cols = key_columns(g.space, g.names, kk[gid.astype(np.int64)])
+            isnull = gid.astype(np.int64) >= len(k)
+            for n_, v in cols.items():
+                v = v.astype(object)
+                v[isnull] = None
+                fdata[n_] = v
+            fdata[f"{fname}_count"] = count_f.cpu().numpy().astype(np.int64)
+            sf = sum_f.cpu().numpy()
+            for j, t in enumerate(targets):
+                fdata[f"{fname}_{t}_sum"] = sf[:, j]
+            fpath = os.path.join(base, f"cat_stats.{fname}.parquet")
+            pd.DataFrame(fdata).to_parquet(fpath)
+            self.stats[fname] = fpath
+
+    def _group(self, name, names) -> _TEGroup:
+        g = self._groups.get(name)
+        if g is not None:
+            return g
+        # a workflow reloaded from disk: rebuild the tables from the cat_stats files
+        import pandas as pd
+        from ._tables import keys_from_frame
+        from ..column import DeviceFrame
+        path = self.stats.get(name)
+        if not isinstance(path, str) or not os.path.exists(path):
+            raise KeyError(name)
+        targets = self.target_columns
+        df = pd.read_parquet(path)
+        space, keys, isnull = keys_from_frame(df, names)
+        dev = keys.device
+        cnt = torch.from_numpy(df[f"{name}_count"].to_numpy(dtype=np.float64)).to(dev)
+        sums = torch.from_numpy(np.stack([df[f"{name}_{t}_sum"].to_numpy(dtype=np.float64) for t in targets],
+                                         axis=1)).to(dev)
+        keep = ~isnull
+        g = _TEGroup(names, space)
+        g.n_groups = int(keep.sum().item())
+        g.has_null = bool(isnull.any().item())
+        kk = keys[keep].contiguous()
+        g.all_vocab = engine.Vocab.from_arrays(kk)
+        nt = len(targets)
+        if g.has_null:
+            ncnt, nsum = cnt[isnull][:1] * 0.0, sums[isnull][:1]
+        else:
+            ncnt, nsum = torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros((1, nt), dtype=torch.float64, device=dev)
+        g._all = (kk, torch.cat([cnt[keep], ncnt]), torch.cat([sums[keep], nsum], dim=0))
+        if self.kfold > 1:
+            fname = _make_name(self.fold_name, *names, sep=self.name_sep)
+            fdf = pd.read_parquet(self.stats[fname])
+            frame = DeviceFrame.from_pandas(fdf[names].reset_index(drop=True))
+            key = space.keys_for([frame[n] for n in names]) if len(names) > 1 else space.keys_for(frame[names[0]])
+            fold = Column(torch.from_numpy(fdf[self.fold_name].to_numpy(dtype=np.int32)).to(dev))
+            fk = engine.pack_keys2(fold, g.gid_for(key)).data
+            g._fold = (fk, torch.from_numpy(fdf[f"{fname}_count"].to_numpy(dtype=np.float64)).to(dev),
+                       torch.from_numpy(np.stack([fdf[f"{fname}_{t}_sum"].to_numpy(dtype=np.float64)
+                                                  for t in targets], axis=1)).to(dev))
+        self._finalize_group(name, g)
+        return g
 
     # ------------------------------------------------------------------ transform
     def transform(self, col_selector: ColumnSelector, df: DeviceFrame) -> DeviceFrame:
@@ -187,7 +272,7 @@ class TargetEncoding(StatOperator):
         out_dtype = np.dtype(self.output_dtype)
         for ind, names in enumerate(self._group_names(col_selector)):
             name = _make_name(*names, sep=self.name_sep)
-            g = self._groups[name]
+            g = self._group(name, names)
             if isinstance(self.out_col, list):
                 if ind >= len(self.out_col):
                     raise ValueError("out_col and cat_groups are different sizes.")
@@ -233,6 +318,9 @@ class TargetEncoding(StatOperator):
         return [Tags.CONTINUOUS]
 
     def set_storage_path(self, new_path, copy=False):
+        if copy:
+            for name, g in list(self._groups.items()):
+                self._write_group(name, g, os.path.join(new_path, "categories"))
         self.out_path = new_path
 
     def clear(self):

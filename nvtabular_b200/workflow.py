@@ -53,11 +53,37 @@ def _execute_node(node: Node, root: DeviceFrame, cache: Dict[int, DeviceFrame]) 
                 names = inp.columns
                 cols = materialize_many([inp[n] for n in names])
                 inp = DeviceFrame(dict(zip(names, cols)))
-            res = node.op.transform(node.input_columns, inp)
+            with _nvtx(f"{type(node.op).__name__}_op"):
+                res = node.op.transform(node.input_columns, inp)
             keep = node.output_columns.names
             out = DeviceFrame({k: res[k] for k in keep if k in res})
     cache[id(node)] = out
     return out
+
+
+class _nvtx:
+    """NVTX range per operator and phase — the reference's @annotate("<Op>_op" / "<Op>_fit",
+    domain="nvt_python") ranges (nvtabular/ops/categorify.py:345,477; ops/clip.py:45), visible in
+    Nsight Systems timelines.  NVTB_NVTX=0 turns them off."""
+    _on = None
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _nvtx._on is None:
+            import torch
+            _nvtx._on = torch.cuda.is_available() and os.environ.get("NVTB_NVTX", "1") != "0"
+        if _nvtx._on:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if _nvtx._on:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def _finalize_frame(frame: DeviceFrame) -> DeviceFrame:
@@ -109,22 +135,13 @@ class Workflow:
             # almost empty stream instead of draining everything Categorify has queued
             ready.sort(key=lambda n: 0 if getattr(n.op, "fit_blocks_host", False) else 1)
             for n in ready:
-                stats = n.op.fit(n.input_columns, _UpstreamPartitions(dataset, n))
-                n.op.fit_finalize(stats)
+                with _nvtx(f"{type(n.op).__name__}_fit"):
+                    stats = n.op.fit(n.input_columns, _UpstreamPartitions(dataset, n))
+                with _nvtx(f"{type(n.op).__name__}_fit_finalize"):
+                    n.op.fit_finalize(stats)
                 fitted.add(id(n))
             stat_nodes = [n for n in stat_nodes if id(n) not in fitted]
         self.fit_schema(dataset.schema)
-        # the reference's fit returns with its vocabulary files on disk: join the writer threads
-        # (they have been working while the GPU ran the vocabulary builds still queued)
-        if not os.environ.get("NVTB_ARTIFACTS_NOWAIT"):
-            self.wait_artifacts()
-        return self
-
-    def wait_artifacts(self) -> "Workflow":
-        """Join the background writes of every op's artefact files (NVTB_ARTIFACTS=eager)."""
-        for n in self.output_node.topo_order():
-            if n.kind == "op" and hasattr(n.op, "wait_artifacts"):
-                n.op.wait_artifacts()
         return self
 
     def fit_schema(self, input_schema: Schema) -> "Workflow":
@@ -158,7 +175,7 @@ class Workflow:
 
     def transform(self, data):
         if isinstance(data, Dataset):
-            return Dataset(data, _transform=self._transform_frame, base_dataset=data.base_dataset,
+            return Dataset(data, _transform=self._transform_frame, base_dataset=data._base_dataset if data._base_dataset is not None else data,
                            schema=self._output_schema)
         if isinstance(data, pd.DataFrame):
             if self._output_schema is None:
@@ -201,31 +218,13 @@ class Workflow:
                 n.selector = ColumnSelector([c for c in n.selector.names if c not in set(input_cols)])
         return self
 
-    # save / load: fitted state only (artefact layout compatibility is SURVEY.md §8f-3)
+    # save / load in the reference's layout: metadata.json + graph.json + artifacts/node_<id>/
+    # (reference nvtabular/workflow/workflow.py:256-348, graph_serializer.py:1077-1165)
     def save(self, path):
-        os.makedirs(path, exist_ok=True)
-        state = []
-        for i, n in enumerate(self.output_node.topo_order()):
-            if n.kind == "op" and isinstance(n.op, StatOperator):
-                n.op.set_storage_path(os.path.join(path, "artifacts", f"node_{i}"), copy=True)
-                st = {k: v for k, v in vars(n.op).items()
-                      if isinstance(v, (int, float, str, bool, type(None), dict, list)) and not k.startswith("_")}
-                if hasattr(n.op, "categories"):
-                    st["categories"] = dict(n.op.categories)
-                state.append({"node": i, "op": type(n.op).__name__, "state": st})
-        with open(os.path.join(path, "fitted_state.json"), "w") as f:
-            json.dump(state, f, default=str)
+        from .serialize import save_workflow
+        save_workflow(self, path)
 
-    def load_state(self, path):
-        with open(os.path.join(path, "fitted_state.json")) as f:
-            state = json.load(f)
-        order = self.output_node.topo_order()
-        for entry in state:
-            op = order[entry["node"]].op
-            for k, v in entry["state"].items():
-                if k == "categories":
-                    for name, p in v.items():
-                        dict.__setitem__(op.categories, name, p)
-                elif hasattr(op, k):
-                    setattr(op, k, v)
-        return self
+    @classmethod
+    def load(cls, path, client=None) -> "Workflow":
+        from .serialize import load_workflow
+        return load_workflow(path, client)

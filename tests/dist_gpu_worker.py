@@ -21,9 +21,14 @@ def main():
     from nvtabular_b200.column import Column, DeviceFrame
     from nvtabular_b200.synth import CAT_NAMES, CONT_NAMES, criteo_frame
 
-    rows = 1 << 20
+    # C1 / C20 at ~2e6 keys with the sorted-accumulator threshold lowered: the key-range exchange
+    # of packed pairs (dist.global_merge_sorted) runs next to the key-hash exchange of the small
+    # columns; odd ranks hold a quarter of the rows, so their C1 / C20 start as hash tables and
+    # are converted (nvtb_hashagg_to_sorted) when the ranks agree on the representation
+    os.environ["NVTB_RUNS_MIN_KEYS"] = "300000"
     cats, conts = CAT_NAMES[:8] + ["C20"], CONT_NAMES[:4]
-    shards = [criteo_frame(rows, total_rows=rows * world, device="cuda", rank=r) for r in range(world)]
+    shards = [criteo_frame((1 << 20) if r % 2 == 0 else (1 << 18), total_rows=40_000_000, device="cuda", rank=r)
+              for r in range(world)]
     mine = shards[rank]
 
     def workflow(path):
@@ -43,6 +48,8 @@ def main():
     os.environ.pop("NVTB_DISABLE_DIST")
 
     cat_op = [n.op for n in wf.output_node.topo_order() if type(n.op).__name__ == "Categorify"][0]
+    modes = {c: cat_op._aggs[c].mode for c in cats}
+    assert modes["C1"] == 1 and modes["C20"] == 1 and modes["C6"] == 0, modes
     ref_op = [n.op for n in ref.output_node.topo_order() if type(n.op).__name__ == "Categorify"][0]
     for c in cats:
         k1, s1 = cat_op.categories.fitted[c].vocab.export()

@@ -60,8 +60,9 @@ def test_movielens_shape_joingroupby_targetencoding_vs_oracle(nvt, ops, tmp_path
         assert out[c].dtype == exp_j[c].dtype, c
         if c.endswith("count"):
             np.testing.assert_array_equal(out[c].to_numpy(), exp_j[c].to_numpy(), err_msg=c)
-        else:       # float32 outputs of fp64 accumulations: one float32 ulp plus the summation order
-            np.testing.assert_allclose(out[c].to_numpy(), exp_j[c].to_numpy(), rtol=3e-6, atol=1e-6,
+        else:       # float32 outputs; pandas accumulates a float32 column IN float32, the engine in fp64:
+            # a few float32 ulps of the partial sums (ratings are multiples of 0.5, so most are exact)
+            np.testing.assert_allclose(out[c].to_numpy(), exp_j[c].to_numpy(), rtol=2e-5, atol=1e-5,
                                        equal_nan=True, err_msg=c)
     exp_t = pd.concat(target_encoding(parts, groups, ["rating"], kfold=5, p_smooth=20)[0], ignore_index=True)
     for c in exp_t.columns:
@@ -89,7 +90,10 @@ def test_target_encoding_random_vs_oracle(nvt, ops, tmp_path, kfold, npartitions
     assert sorted(out.columns) == sorted(exp.columns)
     for c in exp.columns:
         assert out[c].dtype == np.float64
-        np.testing.assert_allclose(out[c].to_numpy(), exp[c].to_numpy(), rtol=1e-9, err_msg=c)
+        # `z` is a float32 column: pandas reduces it (target mean, group sums) in float32, the engine
+        # in fp64 -> a float32 ulp of the mean (3e-8 relative); the float64 target agrees to 1e-9
+        np.testing.assert_allclose(out[c].to_numpy(), exp[c].to_numpy(), rtol=1e-6 if c.endswith("_z") else 1e-9,
+                                   err_msg=c)
 
 
 # C5: HashBucket(2^20) over 40 int64 key columns, keys uniform over 1e8 ids through a 64-bit bijection
