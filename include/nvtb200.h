@@ -41,7 +41,8 @@ typedef enum {
   NVTB_EINVAL = -1,  /* bad argument (dtype, null pointer, size)          */
   NVTB_ENOMEM = -2,  /* device allocation failed                          */
   NVTB_ECUDA = -3,   /* a CUDA runtime call or kernel launch failed       */
-  NVTB_ESTATE = -4   /* handle used in the wrong phase                    */
+  NVTB_ESTATE = -4,  /* handle used in the wrong phase                    */
+  NVTB_ENCCL = -5    /* an NCCL call failed / NCCL is not loadable         */
 } nvtb_status_t;
 
 typedef enum {
@@ -207,6 +208,10 @@ int nvtb_hashagg_export(nvtb_hashagg_t* h, int64_t* keys_out,
  * replacement of the per-partition groupby + concat/groupby tree of reference
  * nvtabular/ops/categorify.py:955-1137 for the C20/C1/C22/C10 class of Criteo columns. */
 int nvtb_hashagg_mode(nvtb_hashagg_t* h, int* mode_host);
+/* A sorted accumulator only COPIES a batch (keys + validity bytes) into its staging buffer; the
+ * sort + run-length encode + merge of everything staged runs when NVTB_STAGE_ROWS rows (default
+ * 2^28) are waiting, when the handle is read (size / export / vocabulary build), or here. */
+int nvtb_hashagg_flush(nvtb_hashagg_t* h, void* stream);
 
 /* ---- sorted-pair primitives of the cross-GPU vocabulary merge --------------
  * A high-cardinality column is exchanged between GPUs as key-ordered packed pairs
@@ -355,6 +360,32 @@ int nvtb_groupstats_gather(const nvtb_groupstats_t* g,
                            const double* miss_vals_host,
                            void* const* out_host, const int* out_dtypes_host,
                            void* stream);
+
+/* ---- cross-GPU collectives of the fit path ---------------------------------
+ * nvtb_comm_t wraps an ncclComm_t: created here (rank 0 makes a unique id, the host runtime
+ * hands it to every rank — torch.distributed broadcast, MPI, a file) or provided by the caller.
+ * These are all the exchanges the path has: moments all-reduce, variable-block all-to-all of
+ * group-by partials, all-gather of vocabulary shards.  They replace the dask tree reduction and
+ * the shared-filesystem broadcast of reference nvtabular/ops/categorify.py:1399-1540, 1627-1643
+ * and ops/moments.py:34-57.  Stream-ordered; NVTB_ENCCL on failure. */
+typedef struct nvtb_comm nvtb_comm_t;
+int nvtb_comm_available(void);
+int nvtb_comm_unique_id(uint8_t* id_out128);
+int nvtb_comm_create(nvtb_comm_t** out, const uint8_t* id128, int rank, int world);
+int nvtb_comm_wrap(nvtb_comm_t** out, void* nccl_comm, int rank, int world);
+int nvtb_comm_destroy(nvtb_comm_t* c);
+int nvtb_comm_rank(const nvtb_comm_t* c, int* rank, int* world);
+/* in place; op: 0 sum, 1 min, 2 max */
+int nvtb_comm_allreduce_f64(nvtb_comm_t* c, double* buf_dev, int64_t n, int op, void* stream);
+int nvtb_comm_allreduce_i64(nvtb_comm_t* c, int64_t* buf_dev, int64_t n, int op, void* stream);
+/* acc_dev: [ncols][5] = {count, sum, sumsq, min, max} (nvtb_moments_accumulate's accumulator) */
+int nvtb_moments_allreduce(nvtb_comm_t* c, double* acc_dev, int ncols, void* stream);
+/* recv holds world blocks of `bytes` bytes in rank order */
+int nvtb_comm_allgather(nvtb_comm_t* c, const void* send_dev, void* recv_dev, int64_t bytes, void* stream);
+/* send_counts_host[r] elements (elem_bytes each, consecutive in send) go to rank r;
+ * recv_counts_host[r] arrive from rank r (consecutive in recv) */
+int nvtb_comm_alltoallv(nvtb_comm_t* c, const void* send_dev, const int64_t* send_counts_host,
+                        void* recv_dev, const int64_t* recv_counts_host, int elem_bytes, void* stream);
 
 /* ---- inference-time transforms on HOST arrays --------------------------------------------
  * The twin of the reference's pybind11 module nvtabular_cpp.inference

@@ -6,7 +6,7 @@ import sys
 import nvtabular_b200 as _impl
 from nvtabular_b200 import *  # noqa: F401,F403
 from nvtabular_b200 import (ColumnSchema, ColumnSelector, Dataset, Schema, Workflow,  # noqa: F401
-                            WorkflowNode, ops)
+                            Shuffle, WorkflowNode, ops)
 
 __version__ = _impl.__version__
 sys.modules.setdefault("nvtabular.ops", ops)

@@ -19,3 +19,11 @@ from .graph import ColumnSchema, ColumnSelector, Node, Schema, Tags  # noqa: F40
 from .workflow import Workflow  # noqa: F401
 
 WorkflowNode = Node
+
+
+class Shuffle:
+    """merlin.io.Shuffle as the reference's benchmark passes it to Dataset.to_parquet
+    (bench/examples/dask-nvtabular-criteo-benchmark.py:225-237)"""
+    PER_PARTITION = "PER_PARTITION"
+    PER_WORKER = "PER_WORKER"
+    FULL = "FULL"

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libnvtb200.so")
-SOURCES = ["scan_kernels.cu", "hashagg.cu", "vocab.cu", "infer.cu"]
+SOURCES = ["scan_kernels.cu", "hashagg.cu", "vocab.cu", "infer.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
         if verbose and out:
             print(out.decode())
     cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC", "-lcudart"]
+           "-Xcompiler", "-fPIC", "-lcudart", "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout.decode()}")

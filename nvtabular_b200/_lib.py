@@ -53,6 +53,7 @@ _SIGNATURES = {
     "nvtb_hashagg_add_null_group": (c_int, [c_void_p, c_int64, POINTER(c_double)]),
     "nvtb_hashagg_size": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p]),
     "nvtb_hashagg_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double), c_void_p]),
+    "nvtb_hashagg_flush": (c_int, [c_void_p, c_void_p]),
     "nvtb_hashagg_mode": (c_int, [c_void_p, POINTER(c_int)]),
     "nvtb_hashagg_to_sorted": (c_int, [c_void_p, c_void_p]),
     "nvtb_hashagg_export_packed": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_void_p]),
@@ -74,6 +75,17 @@ _SIGNATURES = {
     "nvtb_vocab_info": (c_int, [c_void_p, POINTER(nvtb_vocab_info_t)]),
     "nvtb_vocab_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "nvtb_encode_apply": (c_int, [c_void_p, POINTER(nvtb_col_t), c_int64, c_int64, c_int64, c_int64, c_uint64, POINTER(nvtb_col_t), c_int, c_void_p, c_int, c_void_p]),
+    "nvtb_comm_available": (c_int, []),
+    "nvtb_comm_unique_id": (c_int, [c_void_p]),
+    "nvtb_comm_create": (c_int, [POINTER(c_void_p), c_void_p, c_int, c_int]),
+    "nvtb_comm_wrap": (c_int, [POINTER(c_void_p), c_void_p, c_int, c_int]),
+    "nvtb_comm_destroy": (c_int, [c_void_p]),
+    "nvtb_comm_rank": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
+    "nvtb_comm_allreduce_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "nvtb_comm_allreduce_i64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "nvtb_moments_allreduce": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "nvtb_comm_allgather": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "nvtb_comm_alltoallv": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_int, c_void_p]),
     "nvtb_infer_vocab_create": (c_int, [POINTER(c_void_p), c_void_p, c_int64]),
     "nvtb_infer_vocab_from_device": (c_int, [POINTER(c_void_p), c_void_p, c_void_p]),
     "nvtb_infer_vocab_destroy": (c_int, [c_void_p]),

@@ -129,6 +129,7 @@ struct nvtb_hashagg {
   uint8_t* stage_mask;
   int64_t stage_cap;         // rows
   int64_t stage_rows;        // rows waiting (a multiple of 8 except after the last batch)
+  int64_t stage_hint;        // rows the previous fits staged: the buffer grows to hold one whole fit
   cudaEvent_t stage_ev;
   cudaStream_t stage_last;
 };
@@ -1429,14 +1430,17 @@ static int stage_flush(nvtb_hashagg* h, cudaStream_t st) {
 static int stage_append(nvtb_hashagg* h, const int32_t* kp, const uint8_t* mp, int64_t m, cudaStream_t st) {
   if (h->stage_ev == nullptr) NVTB_CUDA_OK(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
   if (h->stage_last != nullptr && h->stage_last != st) NVTB_CUDA_OK(cudaStreamWaitEvent(st, h->stage_ev, 0));
-  if (h->stage_rows + m > h->stage_cap) {
+  const int64_t cap_max = stage_cap_rows();
+  const bool grow_for_fit = h->stage_rows == 0 && h->stage_cap < std::min<int64_t>(cap_max, h->stage_hint);
+  if (h->stage_rows + m > h->stage_cap || grow_for_fit) {
     NVTB_REQUIRE(h->stage_rows == 0, "staging buffer resized while rows are waiting");
     if (h->stage_keys) NVTB_CUDA_OK(cudaFreeAsync(h->stage_keys, st));
     if (h->stage_mask) NVTB_CUDA_OK(cudaFreeAsync(h->stage_mask, st));
     h->stage_keys = nullptr; h->stage_mask = nullptr; h->stage_cap = 0;
     // sized for what the fit has shown so far (a small fit must not pay for 1 GiB), doubling
-    const int64_t cap = stage_cap_rows();
+    const int64_t cap = cap_max;
     int64_t want = std::max<int64_t>((int64_t)1 << 22, next_pow2(2 * (h->rows_total + m)));
+    want = std::max<int64_t>(want, (h->stage_hint + 63) / 64 * 64);      // one flush per fit from the second fit on
     want = std::max<int64_t>(std::min<int64_t>(want, cap), m);
     NVTB_CUDA_OK(cudaMallocAsync(&h->stage_keys, sizeof(int32_t) * (size_t)(want + 64), st));
     NVTB_CUDA_OK(cudaMallocAsync(&h->stage_mask, (size_t)(want / 8 + 64), st));
@@ -1545,6 +1549,7 @@ int nvtb_hashagg_reset(nvtb_hashagg_t* h, void* stream) {
   NVTB_LAUNCH_OK();
   h->u_known = 0;
   h->rows_total = 0;
+  h->stage_hint = std::max<int64_t>(h->stage_hint, h->rows_total);
   h->stage_rows = 0;           // batches still waiting belong to the fit that is being discarded
   h->mailbox_valid = false;
   return NVTB_OK;
@@ -1950,6 +1955,15 @@ int nvtb_segment_copy_u64(const uint64_t* src, uint64_t* dst, const int64_t* seg
       src, dst, reinterpret_cast<const long long*>(seg_src_dev), reinterpret_cast<const long long*>(seg_dst_dev), nseg, n);
   NVTB_LAUNCH_OK();
   return NVTB_OK;
+}
+
+// Sort / run-length encode / merge the batches a sorted accumulator has staged (no-op for a hash
+// table or when nothing is waiting).  Reads of the handle do this implicitly; a caller that
+// wants the cost attributed to the group-by (bench.py) calls it at the end of the last batch.
+int nvtb_hashagg_flush(nvtb_hashagg_t* h, void* stream) {
+  NVTB_REQUIRE(h != nullptr, "NULL handle");
+  if (h->mode != 1 || h->stage_rows == 0) return NVTB_OK;
+  return stage_flush(h, (cudaStream_t)stream);
 }
 
 int nvtb_hashagg_mode(nvtb_hashagg_t* h, int* mode_host) {

@@ -1098,8 +1098,11 @@ static int finish_packed_vocab(nvtb_vocab* v, uint64_t* sorted, int64_t n, int64
   packed_scalars_kernel<<<g, kThreads, 0, st>>>(sorted, n, n_keep, d_sc);
   NVTB_LAUNCH_OK();
   v->info.n_kept = n_keep;
-  // (3) narrow lookup of the kept keys
-  v->t.capacity = pow2_at_least(2 * n_keep);
+  // (3) narrow lookup of the kept keys.  Load 0.31 .. 0.625 of the 4-way buckets (a power of two
+  // at least 1.6 n): these are the vocabularies of 1e7 .. 3e8 keys, where a table twice the size
+  // costs 4 GB more HBM and memset / build traffic per column, while a present key still
+  // resolves in its first bucket more than 9 times out of 10
+  v->t.capacity = pow2_at_least(std::max<int64_t>(n_keep + n_keep * 3 / 5, 64));
   v->t.min_key_pos = -1;
   v->t.narrow = 1;
   NVTB_CUDA_OK(cudaMallocAsync(&v->t.slots, sizeof(int64_t) * v->t.capacity, st));

@@ -315,9 +315,79 @@ class Dataset:
         self.cpu = True
         return self
 
-    def to_parquet(self, output_path, **kwargs):
+    def to_parquet(self, output_path, shuffle=None, out_files_per_proc=None, seed=None, **kwargs):
+        """Write the (lazily transformed) dataset as parquet part files — merlin.io.Dataset.to_parquet
+        as the reference's benchmark calls it (bench/examples/dask-nvtabular-criteo-benchmark.py:225-237;
+        semantics bench/examples/MultiGPUBench.md:75-89):
+
+          shuffle=None | False        one file per partition, rows in input order
+          shuffle="PER_PARTITION"     the rows of every partition are permuted on the device
+                                      (torch.randperm + one gather per column) before the D2H copy
+          shuffle="PER_WORKER"        every row goes to one of `out_files_per_proc` files of this
+                                      process (uniformly at random) and each file is permuted as a
+                                      whole when it is closed: the shuffle across partitions that the
+                                      reference's per-worker writer cache (nvtabular/worker.py) does
+
+        Under torch.distributed every rank writes its own files (`part_<rank>_<i>.parquet`)."""
+        import pyarrow as pa
         import pyarrow.parquet as pq
+        from .dist import world
         os.makedirs(output_path, exist_ok=True)
-        for i, part in enumerate(self.partitions()):
-            pq.write_table(part.to_arrow(), os.path.join(output_path, f"part_{i}.parquet"))
+        mode = getattr(shuffle, "name", shuffle)
+        mode = str(mode).upper() if mode not in (None, False) else None
+        if mode not in (None, "PER_PARTITION", "PER_WORKER", "FULL"):
+            raise ValueError(f"unknown shuffle mode {shuffle!r}")
+        w, rank = world()
+        prefix = f"part_{rank}_" if w > 1 else "part_"
+        gen = None
+        if mode is not None and torch.cuda.is_available():
+            gen = torch.Generator(device="cuda")
+            gen.manual_seed(int(seed if seed is not None else 0x5EED) + rank)
+        if mode in (None, "PER_PARTITION"):
+            for i, part in enumerate(self.partitions()):
+                if mode == "PER_PARTITION" and len(part):
+                    part = _permute_rows(part, torch.randperm(len(part), generator=gen, device="cuda"))
+                pq.write_table(part.to_arrow(), os.path.join(output_path, f"{prefix}{i}.parquet"))
+            return output_path
+        nfiles = int(out_files_per_proc or 1)
+        buckets = [[] for _ in range(nfiles)]
+        for part in self.partitions():
+            n = len(part)
+            if n == 0:
+                continue
+            dest = torch.randint(0, nfiles, (n,), generator=gen, device="cuda")
+            order = torch.argsort(dest, stable=True)
+            counts = torch.bincount(dest, minlength=nfiles).cpu().tolist()
+            tab = _permute_rows(part, order).to_arrow()
+            off = 0
+            for f, c in enumerate(counts):
+                if c:
+                    buckets[f].append(tab.slice(off, c))
+                off += c
+        rng = np.random.default_rng(int(seed if seed is not None else 0x5EED) + 7919 * (rank + 1))
+        for f, chunks in enumerate(buckets):
+            if not chunks:
+                continue
+            tab = pa.concat_tables(chunks)
+            tab = tab.take(pa.array(rng.permutation(len(tab))))
+            pq.write_table(tab, os.path.join(output_path, f"{prefix}{f}.parquet"))
         return output_path
+
+
+def _permute_rows(frame: DeviceFrame, perm: torch.Tensor) -> DeviceFrame:
+    """frame[perm] for flat columns (data + validity); list columns are not shuffled row-wise here"""
+    from .column import pack_validity, unpack_validity
+    out = {}
+    n = len(frame)
+    for name, c in frame.items():
+        if c.offsets is not None:
+            raise NotImplementedError("shuffling list columns")
+        from .ops.fill import materialize
+        c = materialize(c)
+        v = None
+        if c.validity is not None:
+            v = pack_validity(unpack_validity(c.validity, n)[perm])
+        col = Column(c.data[perm], v, None, c.dictionary, None, c.is_bool)
+        col.prehashed = c.prehashed
+        out[name] = col
+    return DeviceFrame(out)

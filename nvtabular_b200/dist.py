@@ -40,6 +40,100 @@ def all_gather_object(obj):
     return out
 
 
+# ---------------------------------------------------------------------------------------
+# transport: the library's own NCCL communicator (csrc/comm.cu, nvtb_comm_t) when the process
+# group runs on NCCL — torch.distributed then only carries the 128-byte unique id and host
+# metadata; gloo (CPU tests) and NVTB_COMM=torch go through torch.distributed's collectives
+# ---------------------------------------------------------------------------------------
+_NATIVE = {"comm": None, "tried": False}
+
+
+def native_comm():
+    """-> ctypes handle of this process group's nvtb_comm_t, or None"""
+    import ctypes
+    import os
+    import torch.distributed as dist
+    if _NATIVE["tried"]:
+        return _NATIVE["comm"]
+    _NATIVE["tried"] = True
+    w, rank = world()
+    if w <= 1 or os.environ.get("NVTB_COMM", "native").lower() == "torch" or not dist.is_initialized() \
+            or dist.get_backend() != "nccl" or not torch.cuda.is_available():
+        return None
+    from . import _lib
+    lib = _lib.load()
+    if not lib.nvtb_comm_available():
+        return None
+    buf = (ctypes.c_uint8 * 128)()
+    if rank == 0:
+        _lib.check(lib.nvtb_comm_unique_id(buf))
+    box = [bytes(buf)]
+    dist.broadcast_object_list(box, src=0)
+    buf = (ctypes.c_uint8 * 128).from_buffer_copy(box[0])
+    h = ctypes.c_void_p()
+    _lib.check(lib.nvtb_comm_create(ctypes.byref(h), buf, rank, w))
+    _NATIVE["comm"] = (lib, h)
+    return _NATIVE["comm"]
+
+
+def reset_native_comm():
+    nc = _NATIVE["comm"]
+    if nc is not None:
+        nc[0].nvtb_comm_destroy(nc[1])
+    _NATIVE["comm"], _NATIVE["tried"] = None, False
+
+
+def alltoallv(send: torch.Tensor, send_counts, recv_counts) -> torch.Tensor:
+    """variable-block all-to-all of a 1-D tensor: send_counts[r] elements go to rank r"""
+    import ctypes
+    import torch.distributed as dist
+    from . import _lib
+    recv = torch.empty(sum(recv_counts), dtype=send.dtype, device=send.device)
+    nc = native_comm()
+    if nc is not None and send.is_cuda:
+        lib, h = nc
+        sc = (ctypes.c_int64 * len(send_counts))(*[int(x) for x in send_counts])
+        rc = (ctypes.c_int64 * len(recv_counts))(*[int(x) for x in recv_counts])
+        send = send.contiguous()
+        _lib.check(lib.nvtb_comm_alltoallv(h, ctypes.c_void_p(send.data_ptr()), sc, ctypes.c_void_p(recv.data_ptr()), rc,
+                                           send.element_size(), _lib.stream_ptr()))
+        return recv
+    dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=[int(x) for x in recv_counts],
+                           input_split_sizes=[int(x) for x in send_counts])
+    return recv
+
+
+def allgather_equal(t: torch.Tensor) -> torch.Tensor:
+    """all-gather of equal-sized 1-D blocks -> [world * n] in rank order"""
+    import ctypes
+    import torch.distributed as dist
+    from . import _lib
+    w, _ = world()
+    t = t.contiguous()
+    out = torch.empty(w * t.numel(), dtype=t.dtype, device=t.device)
+    nc = native_comm()
+    if nc is not None and t.is_cuda:
+        lib, h = nc
+        _lib.check(lib.nvtb_comm_allgather(h, ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                           t.numel() * t.element_size(), _lib.stream_ptr()))
+        return out
+    dist.all_gather_into_tensor(out, t)
+    return out
+
+
+def allreduce_sum_i64(t: torch.Tensor) -> torch.Tensor:
+    import ctypes
+    import torch.distributed as dist
+    from . import _lib
+    nc = native_comm()
+    if nc is not None and t.is_cuda:
+        lib, h = nc
+        _lib.check(lib.nvtb_comm_allreduce_i64(h, ctypes.c_void_p(t.data_ptr()), t.numel(), 0, _lib.stream_ptr()))
+        return t
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
 def exchange_by_owner(keys, sizes, vals, perm, counts):
     """all-to-all of rows already grouped by owner (perm/counts from
     nvtb_partition_by_owner).  Returns the rows this rank owns."""
@@ -188,10 +282,8 @@ def global_merge_many(aggs, engine=None, owner_pool=None):
     cm_recv_h = cm_recv.view(w, nc).cpu()
     in_split = [int(x) for x in counts.sum(dim=1).tolist()]
     out_split = [int(x) for x in cm_recv_h.sum(dim=1).tolist()]
-    rk = torch.empty(sum(out_split), dtype=torch.int64, device=dev)
-    rs = torch.empty(sum(out_split), dtype=torch.int64, device=dev)
-    dist.all_to_all_single(rk, sk, output_split_sizes=out_split, input_split_sizes=in_split)
-    dist.all_to_all_single(rs, ss, output_split_sizes=out_split, input_split_sizes=in_split)
+    rk = alltoallv(sk, in_split, out_split)
+    rs = alltoallv(ss, in_split, out_split)
     mark("all_to_all")
     # 3. owner merge per column (exact global sizes over disjoint keys)
     src_off = [0]
@@ -238,10 +330,8 @@ def global_merge_many(aggs, engine=None, owner_pool=None):
     if tot[rank]:
         pk[: tot[rank]] = torch.cat(owned_k)
         ps[: tot[rank]] = torch.cat(owned_s)
-    gk = torch.empty(w * mx, dtype=torch.int64, device=dev)
-    gs = torch.empty(w * mx, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(gk, pk)
-    dist.all_gather_into_tensor(gs, ps)
+    gk = allgather_equal(pk)
+    gs = allgather_equal(ps)
     ns = torch.tensor([e[3] for e in exported], dtype=torch.int64, device=dev)
     dist.all_reduce(ns, op=dist.ReduceOp.SUM)
     ns_h = ns.cpu().tolist()
@@ -266,7 +356,7 @@ def global_merge_many(aggs, engine=None, owner_pool=None):
 # =======================================================================================
 # High-cardinality columns: key-RANGE exchange of sorted packed pairs
 # =======================================================================================
-def global_merge_sorted(aggs, engine=None):
+def global_merge_sorted(aggs, engine=None, device=None):
     """Cross-GPU merge of int32 key-count columns held as SORTED accumulators (key-ordered packed
     pairs word = (key ^ 2^31) << 32 | count; csrc/sortagg.cuh).  Returns, per column,
     (ordered_pairs, null_size): the GLOBAL vocabulary in (count desc, key asc) order, identical
@@ -299,11 +389,11 @@ def global_merge_sorted(aggs, engine=None):
     out = []
     if not aggs:
         return out
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
     sizes = [a.size() for a in aggs]                      # (n_unique, null_size) per column
     ns = torch.tensor([s[1] for s in sizes], dtype=torch.int64, device=dev)
     if w > 1:
-        dist.all_reduce(ns, op=dist.ReduceOp.SUM)
+        allreduce_sum_i64(ns)
     ns_h = [int(x) for x in ns.cpu().tolist()]
     for c, agg in enumerate(aggs):
         t0 = time.perf_counter()
@@ -318,9 +408,7 @@ def global_merge_sorted(aggs, engine=None):
             if n:
                 idx = (torch.arange(1, w, device=dev, dtype=torch.int64) * n) // w
                 q[1:] = (p[idx] >> 32) & 0xFFFFFFFF
-            allq = torch.empty(w * w, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(allq, q)
-            allq = allq.view(w, w)
+            allq = allgather_equal(q).view(w, w)
             live = (allq[:, 0] > 0).to(torch.float64)
             nlive = live.sum().clamp(min=1.0)
             spl = torch.floor((allq[:, 1:].to(torch.float64) * live[:, None]).sum(dim=0) / nlive).to(torch.int64)
@@ -328,13 +416,11 @@ def global_merge_sorted(aggs, engine=None):
             edges = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), lb,
                                torch.full((1,), n, dtype=torch.int64, device=dev)])
             send_counts = edges[1:] - edges[:-1]
-            recv_counts = torch.empty_like(send_counts)
-            dist.all_to_all_single(recv_counts, send_counts)
-            sc_h = [int(x) for x in send_counts.cpu().tolist()]
-            rc_h = [int(x) for x in recv_counts.cpu().tolist()]
+            all_counts = allgather_equal(send_counts).view(w, w).cpu()       # [source, owner]
+            sc_h = [int(x) for x in all_counts[rank].tolist()]
+            rc_h = [int(x) for x in all_counts[:, rank].tolist()]
             # 2. one all-to-all of packed pairs, then the owner's pairwise merges
-            recv = torch.empty(sum(rc_h), dtype=torch.int64, device=dev)
-            dist.all_to_all_single(recv, p, output_split_sizes=rc_h, input_split_sizes=sc_h)
+            recv = alltoallv(p, sc_h, rc_h)
             del p
             runs, off = [], 0
             for r in range(w):
@@ -371,18 +457,14 @@ def global_merge_sorted(aggs, engine=None):
             continue
         # 4. small tables -> destination of every (owner, count value) group
         meta = torch.tensor([vals.numel(), n_s], dtype=torch.int64, device=dev)
-        allmeta = torch.empty(2 * w, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allmeta, meta)
-        allmeta_h = allmeta.view(w, 2).cpu()
+        allmeta_h = allgather_equal(meta).view(w, 2).cpu()
         d_all = [int(x) for x in allmeta_h[:, 0].tolist()]
         n_all = [int(x) for x in allmeta_h[:, 1].tolist()]
         d_max, n_max, n_glob = max(max(d_all), 1), max(max(n_all), 1), sum(n_all)
         tab = torch.zeros(2 * d_max, dtype=torch.int64, device=dev)
         tab[: vals.numel()] = vals
         tab[d_max: d_max + lens.numel()] = lens
-        alltab = torch.empty(w * 2 * d_max, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(alltab, tab)
-        alltab = alltab.view(w, 2, d_max)
+        alltab = allgather_equal(tab).view(w, 2, d_max)
         g_val, g_len, g_src, pad_src = [], [], [], []
         for r in range(w):                                  # groups listed owner-major
             g_val.append(alltab[r, 0, : d_all[r]])
@@ -409,15 +491,14 @@ def global_merge_sorted(aggs, engine=None):
         padded = torch.zeros(n_max, dtype=torch.int64, device=dev)
         padded[:n_s] = C
         del C
-        gathered = torch.empty(w * n_max, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(gathered, padded)
+        gathered = allgather_equal(padded)
         del padded
         ordered = torch.empty(n_glob, dtype=torch.int64, device=dev)
         if n_glob:
             engine.segment_copy(gathered, ordered, seg_src, seg_dst)
         del gathered
         out.append((ordered, ns_h[c]))
-        if trace and rank == 0:
+        if trace and rank == 0 and dev.type == "cuda":
             torch.cuda.synchronize()
             t2 = time.perf_counter()
             print(f"[nvtb trace] merge_sorted col {c}: local {n} pairs, shard {n_s}, global {n_glob}; "

@@ -110,8 +110,13 @@ class Moments:
         """Cross-GPU merge: one NCCL all-reduce of 3 sums + min + max per column
         (replaces the dask tree of moments.py:45-55)."""
         import torch.distributed as dist
-        from .dist import world
+        from .dist import native_comm, world
         if world()[0] <= 1:
+            return
+        nc = native_comm()
+        if nc is not None and self.acc.is_cuda:            # the library's own communicator (csrc/comm.cu)
+            _lib.check(nc[0].nvtb_moments_allreduce(nc[1], _ptr(self.acc), self.ncols, _lib.stream_ptr()))
+            _count()
             return
         a = self.acc.view(self.ncols, 5)
         sums = a[:, 0:3].contiguous()
@@ -281,6 +286,12 @@ class HashAgg:
         m = c_int(0)
         _lib.check(self.lib.nvtb_hashagg_mode(self.h, byref(m)))
         return m.value
+
+    def flush(self):
+        """fold in whatever a sorted accumulator has staged (timed with the inserts: it is their cost)"""
+        with _timed("hashagg_insert", 0.0):
+            _lib.check(self.lib.nvtb_hashagg_flush(self.h, _lib.stream_ptr()))
+        _count(12)
 
     def to_sorted(self):
         """make the handle a sorted accumulator (key-ordered packed pairs), see csrc/sortagg.cuh"""

@@ -34,12 +34,32 @@ def keys_from_frame(df: pd.DataFrame, key_names: List[str]) -> Tuple[object, tor
 
 
 def key_columns(space, key_names: List[str], keys: np.ndarray, with_null_row: bool = False) -> dict:
-    """decoded key columns of a table ({name: Series}); `with_null_row` appends the null group"""
+    """decoded key columns of a table ({name: Series}); `with_null_row` appends the null group.
+    The dtype of the key survives the null: integers become pandas nullable integers (parquet
+    then holds an int column with a null, as cuDF writes it — not float64), floats get NaN,
+    strings None."""
     comps = space.decode(keys) if isinstance(space, ComboKeySpace) else [space.decode(keys)]
     out = {}
     for name, v in zip(key_names, comps):
-        v = pd.Series(v, dtype=object if getattr(v, "dtype", None) == object else None)
+        v = np.asarray(v)
+        if v.dtype == object:
+            isn = np.array([x is None for x in v], dtype=bool)
+            vals = [x for x in v if x is not None]
+            if vals and all(isinstance(x, (int, np.integer)) for x in vals):       # ints with nulls (combo decode)
+                arr = pd.array([pd.NA if m else int(x) for x, m in zip(v, isn)], dtype="Int64")
+                ser = pd.Series(arr)
+            else:
+                ser = pd.Series(v, dtype=object)
+        else:
+            ser = pd.Series(v)
         if with_null_row:
-            v = pd.concat([v.astype(object), pd.Series([None], dtype=object)], ignore_index=True)
-        out[name] = v
+            if ser.dtype == object:
+                ser = pd.concat([ser, pd.Series([None], dtype=object)], ignore_index=True)
+            elif pd.api.types.is_integer_dtype(ser.dtype):
+                name_dt = ser.dtype.name if pd.api.types.is_extension_array_dtype(ser.dtype) else \
+                    ser.dtype.name.replace("int", "Int").replace("uInt", "UInt")
+                ser = pd.concat([ser.astype(name_dt), pd.Series(pd.array([pd.NA], dtype=name_dt))], ignore_index=True)
+            else:
+                ser = pd.concat([ser, pd.Series([np.nan], dtype=ser.dtype)], ignore_index=True)
+        out[name] = ser
     return out

@@ -209,7 +209,8 @@ class FittedVocab:
                 if self.vocab.n_total == 0:   # categorify.py:1318-1324: empty input -> a single null row
                     df = pd.DataFrame({n: pd.Series([None], dtype=object) for n in self.key_names})
                 df.to_parquet(upath, compression=None)
-            self._written = True
+            if self.path is None or os.path.abspath(upath) == os.path.abspath(self.path):
+                self._written = True
 
     def wait(self):
         """kept for callers of the earlier threaded writer: writes are synchronous now"""
@@ -426,6 +427,10 @@ class Categorify(StatOperator):
                     for n in names:
                         self._insert(storage, agg, space.keys_for(part[n]))
                 part = next(it, None)
+            for storage, _ in groups:                       # staged batches of the sorted accumulators
+                flush = getattr(state[storage][1], "flush", None)
+                if flush is not None:
+                    flush()
             if world()[0] == 1:
                 # single GPU: every vocabulary is built straight from its handle — the small ones
                 # first, their keys / sizes on the way to pinned host memory (artefact files)
@@ -593,10 +598,17 @@ class Categorify(StatOperator):
             self.categories[name] = fv.path
             self.categories.fitted[name] = fv
 
-    def wait_artifacts(self):
-        """join the background writes of this op's vocabulary files (NVTB_ARTIFACTS=eager)"""
-        for fv in self.categories.fitted.values():
-            fv.wait()
+    def export_artifacts(self, new_path) -> Dict[str, str]:
+        """write unique.<name>.parquet / meta.<name>.parquet of every vocabulary under
+        new_path/categories WITHOUT re-pointing this op (Workflow.save); -> {storage name: path}"""
+        base = os.path.join(new_path, "categories")
+        os.makedirs(base, exist_ok=True)
+        out = {}
+        for name in list(self.categories):
+            fv = self._fitted(name)
+            fv._write_now(base, True)
+            out[name] = "/".join([base, f"unique.{fv.name}.parquet"])
+        return out
 
     def set_storage_path(self, new_path, copy=False):
         for name, fv in self.categories.fitted.items():

@@ -66,20 +66,11 @@ class GroupTable:
         return t
 
     def frame(self) -> pd.DataFrame:
+        from ._tables import key_columns
         k = self.keys.cpu().numpy()
-        if isinstance(self.space, ComboKeySpace):
-            comps = self.space.decode(k)
-        else:
-            comps = [self.space.decode(k)]
         st = self.stats.cpu().numpy()
-        data = {}
-        n = len(k)
-        for name, v in zip(self.key_names, comps):
-            v = pd.Series(v, dtype=object if v.dtype == object else None)
-            if self.null_row >= 0:
-                v = pd.concat([v, pd.Series([None], dtype=object)], ignore_index=True)
-            data[name] = v
-        rows = n + (1 if self.null_row >= 0 else 0)
+        data = key_columns(self.space, self.key_names, k, with_null_row=self.null_row >= 0)
+        rows = len(k) + (1 if self.null_row >= 0 else 0)
         f32 = getattr(self, "f32_stats", ())
         for j, sn in enumerate(self.stat_names):
             col = st[:rows, j]
@@ -90,11 +81,38 @@ class GroupTable:
             data[sn] = col
         return pd.DataFrame(data)
 
-    def write(self, base):
+    def write(self, base, force=True):
+        """cat_stats.<name>.parquet (categorify.py:1500-1503).  Tables above 2^20 groups are written
+        when their path is first read (`op.categories[name]`, Workflow.save): decoding tens of
+        millions of group keys on the host is seconds of pandas work the transform never needs —
+        the same rule as Categorify's large vocabulary files."""
         os.makedirs(base, exist_ok=True)
         self.path = os.path.join(base, f"cat_stats.{self.name}.parquet")
-        self.frame().to_parquet(self.path)
+        lazy = os.environ.get("NVTB_ARTIFACTS", "eager").lower() == "lazy"
+        if force or (not lazy and self.keys.numel() <= (1 << 20)):
+            self.frame().to_parquet(self.path)
+            self._written = True
+        else:
+            self._written = False
         return self.path
+
+    def ensure_written(self):
+        if self.path is not None and not getattr(self, "_written", True):
+            self.write(os.path.dirname(self.path), force=True)
+
+
+class _StatPaths(dict):
+    """group name -> cat_stats path; reading a path makes sure a deferred file exists"""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.tables = {}
+
+    def __getitem__(self, key):
+        t = self.tables.get(key)
+        if t is not None:
+            t.ensure_written()
+        return super().__getitem__(key)
 
 
 def build_group_table(name, key_names, space, agg: engine.HashAgg, cont_names, stats, sep="_") -> GroupTable:
@@ -157,7 +175,7 @@ class JoinGroupby(StatOperator):
         self.out_path = out_path or "./"
         self.on_host = on_host
         self.cat_cache = cat_cache
-        self.categories: Dict[str, str] = {}
+        self.categories: Dict[str, str] = _StatPaths()
         self.tables: Dict[str, GroupTable] = {}
         self._cont_names = None
         if isinstance(cont_cols, Node):
@@ -201,7 +219,9 @@ class JoinGroupby(StatOperator):
         base = os.path.join(self.out_path, "categories")
         for name, t in tables.items():
             self.tables[name] = t
-            self.categories[name] = t.write(base)
+            self.categories[name] = t.write(base, force=False)
+            if isinstance(self.categories, _StatPaths):
+                self.categories.tables[name] = t
 
     def transform(self, col_selector: ColumnSelector, df: DeviceFrame) -> DeviceFrame:
         new_df = DeviceFrame()
@@ -264,6 +284,19 @@ class JoinGroupby(StatOperator):
                 break
         return new_schema.with_dtype(dtype, False, False)
 
+    def export_tables(self, new_path) -> Dict[str, str]:
+        """write every group table under new_path/categories WITHOUT re-pointing this op
+        (Workflow.save); -> {group name: path}"""
+        base = os.path.join(new_path, "categories")
+        os.makedirs(base, exist_ok=True)
+        out = {}
+        for name in list(self.categories):
+            t = self._table(name)
+            p = os.path.join(base, f"cat_stats.{name}.parquet")
+            t.frame().to_parquet(p)
+            out[name] = p
+        return out
+
     def set_storage_path(self, new_path, copy=False):
         for name, t in self.tables.items():
             if copy:
@@ -271,7 +304,7 @@ class JoinGroupby(StatOperator):
         self.out_path = new_path
 
     def clear(self):
-        self.categories = {}
+        self.categories = _StatPaths()
         self.tables = {}
         self.storage_name = {}
 

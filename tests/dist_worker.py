@@ -119,6 +119,68 @@ def main():
         o = np.argsort(mk.numpy())
         res["many"].append({"keys": mk.numpy()[o].tolist(), "sizes": ms.numpy()[o].tolist(), "null": mns})
     res["many_local"] = local_cols
+    # high-cardinality path: key-range exchange of sorted packed pairs (dist.global_merge_sorted)
+    # with numpy stand-ins for the device primitives
+    from nvtabular_b200.dist import global_merge_sorted
+
+    class PackedAgg:
+        def __init__(self, keys_i32, nulls):
+            u, c = np.unique(keys_i32.astype(np.int64), return_counts=True)
+            uk = (u + (1 << 31)).astype(np.uint64)                     # key ^ 2^31 == key + 2^31 for int32
+            self.pairs = torch.from_numpy(((uk << np.uint64(32)) | c.astype(np.uint64)).view(np.int64))
+            self.nulls = nulls
+
+        def size(self):
+            return self.pairs.numel(), self.nulls
+
+        def export_packed(self, device=None):
+            return self.pairs.clone()
+
+    def _u(t):
+        return t.numpy().view(np.uint64)
+
+    class SortedEngine:
+        @staticmethod
+        def pairs_lower_bounds(pairs, bounds):
+            k = _u(pairs) >> np.uint64(32)
+            return torch.from_numpy(np.searchsorted(k, bounds.numpy().astype(np.uint64), side="left").astype(np.int64))
+
+        @staticmethod
+        def pairs_merge(a, b):
+            w = np.concatenate([_u(a), _u(b)])
+            k, c = w >> np.uint64(32), w & np.uint64(0xFFFFFFFF)
+            uk, inv = np.unique(k, return_inverse=True)
+            cs = np.zeros(len(uk), dtype=np.uint64)
+            np.add.at(cs, inv, c)
+            return torch.from_numpy(((uk << np.uint64(32)) | cs).view(np.int64))
+
+        @staticmethod
+        def radix_sort(data, lo_bit=0, hi_bit=None, descending=False):
+            w = _u(data)
+            f = (w >> np.uint64(lo_bit)) & np.uint64((1 << (hi_bit - lo_bit)) - 1)
+            order = np.argsort(-f.astype(np.int64) if descending else f.astype(np.int64), kind="stable")
+            return torch.from_numpy(w[order].view(np.int64))
+
+        @staticmethod
+        def segment_copy(src, dst, seg_src, seg_dst):
+            ss, sd = seg_src.tolist(), seg_dst.tolist()
+            for j in range(len(sd)):
+                if sd[j] >= 0:
+                    n = ss[j + 1] - ss[j]
+                    dst[sd[j]: sd[j] + n] = src[ss[j]: ss[j + 1]]
+
+    big_local = []
+    big = []
+    for c in range(2):
+        kk = (rng.integers(0, 4000 * (c + 1), 9000 + 1000 * rank) * 2654435761 % (1 << 31) - (1 << 30) * c).astype(np.int32)
+        big_local.append(kk.tolist())
+        big.append(PackedAgg(kk, 3 + c + rank))
+    res["sorted"] = []
+    for ordered, nsz in global_merge_sorted(big, engine=SortedEngine, device=torch.device("cpu")):
+        w = _u(ordered)
+        res["sorted"].append({"keys": ((w >> np.uint64(32)).astype(np.int64) - (1 << 31)).tolist(),
+                              "sizes": (w & np.uint64(0xFFFFFFFF)).astype(np.int64).tolist(), "null": nsz})
+    res["sorted_local"] = big_local
     t = allgather_var(torch.arange(rank + 2, dtype=torch.int64))
     res["allgather_var"] = t.tolist()
     with open(os.path.join(out_dir, f"rank{rank}.json"), "w") as f:

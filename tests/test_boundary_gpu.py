@@ -163,3 +163,41 @@ def test_inference_hooks(nvt, tmp_path):
     np.testing.assert_allclose(np.asarray(got["x"].cpu() if hasattr(got["x"], "cpu") else got["x"]), exp["x"].to_numpy(),
                                rtol=1e-12)
     assert norm_op.supported_formats is not None and cat_op.supported_formats is not None
+
+
+def test_parquet_ingest_transform_egress_with_shuffle(nvt, tmp_path):
+    """parquet -> device partitions -> Workflow -> to_parquet: the row-group
+    reader keeps nullable int32 as int32 + bitmask; PER_PARTITION / PER_WORKER shuffles write
+    a permutation of exactly the unshuffled rows (reference bench/examples/MultiGPUBench.md:75-89)."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    rng = np.random.default_rng(8)
+    n = 30_000
+    a = pd.array(rng.integers(0, 300, n), dtype="Int32")
+    a[rng.random(n) < 0.1] = pd.NA
+    df = pd.DataFrame({"a": a, "x": rng.normal(0, 1, n), "rid": np.arange(n, dtype=np.int64)})
+    src = tmp_path / "in.parquet"
+    pq.write_table(pa.Table.from_pandas(df, preserve_index=False), src, row_group_size=7000)
+    ops = nvt.ops
+    wf = nvt.Workflow((["a"] >> ops.Categorify(out_path=str(tmp_path / "c"))) + (["x"] >> ops.Normalize()) + ["rid"])
+    ds = nvt.Dataset(str(src))
+    assert ds.npartitions == 5                                   # one partition per row group
+    wf.fit(ds)
+    base = wf.transform(ds).to_ddf().compute()
+    assert base["rid"].tolist() == list(range(n))
+    exp = wf.transform(nvt.Dataset(df)).to_ddf().compute()      # the pandas path sees the same rows
+    np.testing.assert_array_equal(base["a"].to_numpy(), exp["a"].to_numpy())
+    for mode, kw in [(None, {}), ("PER_PARTITION", {}), (nvt.Shuffle.PER_WORKER, {"out_files_per_proc": 3})]:
+        out_dir = tmp_path / f"out_{mode}"
+        wf.transform(ds).to_parquet(str(out_dir), shuffle=mode, **kw)
+        files = sorted(os.listdir(out_dir))
+        assert len(files) == (3 if mode == "PER_WORKER" else 5)
+        got = pd.concat([pd.read_parquet(out_dir / f) for f in files], ignore_index=True)
+        assert len(got) == n
+        if mode is None:
+            assert got["rid"].tolist() == list(range(n))
+        else:
+            assert got["rid"].tolist() != list(range(n))
+        got = got.sort_values("rid", ignore_index=True)
+        np.testing.assert_array_equal(got["a"].to_numpy(), base["a"].to_numpy())
+        np.testing.assert_array_equal(got["x"].to_numpy(), base["x"].to_numpy())

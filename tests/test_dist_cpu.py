@@ -44,3 +44,13 @@ def test_owner_exchange_two_ranks_gloo(tmp_path):
         assert res[0]["many"][c]["keys"] == vc.index.tolist()
         assert res[0]["many"][c]["sizes"] == vc.tolist()
         assert res[0]["many"][c]["null"] == 2 * c + 1
+    # key-range exchange of sorted pairs: identical on both ranks, and exactly the union's
+    # value_counts in (count desc, key asc) order — the order the vocabulary is built in
+    assert res[0]["sorted"] == res[1]["sorted"]
+    for c in range(2):
+        vc = pd.Series(res[0]["sorted_local"][c] + res[1]["sorted_local"][c]).value_counts(sort=False)
+        exp = pd.DataFrame({"k": vc.index.to_numpy(), "s": vc.to_numpy()}).sort_values(
+            ["s", "k"], ascending=[False, True], kind="stable")
+        assert res[0]["sorted"][c]["keys"] == exp["k"].tolist()
+        assert res[0]["sorted"][c]["sizes"] == exp["s"].tolist()
+        assert res[0]["sorted"][c]["null"] == 2 * (3 + c) + 1

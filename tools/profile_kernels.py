@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--which", default="insert,encode,moments,normalize")
     ap.add_argument("--cards", default="3,1543,39043,100000,1766023")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--batches", type=int, default=2)
     a = ap.parse_args()
     which = a.which.split(",")
     cards = [int(x) for x in a.cards.split(",")]
@@ -39,15 +40,17 @@ def main():
             agg = engine.HashAgg(0, capacity_hint=k)
             for _ in range(a.reps):
                 agg.reset()
-                agg.insert(col)
-            keys, sizes, _, ns, _ = agg.export()
+                for b in range(a.batches):        # a fit = several batches (sorted accumulators stage them)
+                    agg.insert(col)
+            # the vocabulary straight from the handle: the path Categorify.fit takes on one GPU
+            v = engine.Vocab.build_from_agg(agg, key_bits=32, size_bound=a.rows * a.batches)
             torch.cuda.synchronize()
-            print(f"card {k}: {keys.numel()} uniques, null {ns}")
+            print(f"card {k}: mode {agg.mode}, {v.n_kept} kept keys, null {v.null_size}")
         if "encode" in which:
-            v = engine.Vocab.build(keys, sizes, ns)
             for _ in range(a.reps):
                 out = v.encode(col, 1, 2, 3)
             torch.cuda.synchronize()
+            del out
     if "moments" in which or "normalize" in which:
         g = torch.Generator(device="cuda"); g.manual_seed(7)
         cols = []
