@@ -301,7 +301,7 @@ part_hist_kernel(const int32_t* __restrict__ keys, const uint8_t* __restrict__ m
   __syncthreads();
   for (int d = threadIdx.x; d < P; d += kPartThreads)
     if (cnt[d]) atomicAdd(&total[d], cnt[d]);
-  if (threadIdx.x == 0 && s_null) atomicAdd(&ctr->size[0], (unsigned long long)s_null);
+  if (threadIdx.x == 0 && s_null && ctr != nullptr) atomicAdd(&ctr->size[0], (unsigned long long)s_null);
 }
 
 // exclusive scan of `vals[0..P)` held in shared memory, P % T == 0; every value is first

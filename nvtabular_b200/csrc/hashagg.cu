@@ -316,6 +316,7 @@ namespace nvtb {
 constexpr int kExportPerThread = 4;
 }
 #include "sortagg.cuh"
+#include "bucketagg.cuh"
 namespace nvtb {
 
 // ---------------------------------------------------------------------------
@@ -1248,7 +1249,9 @@ static int sort_scratch_acquire(int64_t m, int64_t n_pairs_sort, int64_t mt, cud
   const int P = 1 << kSortLowBits;
   const size_t rx_bytes = align_up(std::max(rx_scratch_bytes<uint32_t>(m, kRxMaxStableBits - 1),
                                             rx_scratch_bytes<uint64_t>(n_pairs_sort, kRxMaxStableBits - 1)), 256);
-  const size_t meta_bytes = align_up(sizeof(uint32_t) * 3 * P, 256);
+  // radix path: total[P] | starts[P] | cursor[P]; bucket path (bucketagg.cuh): the same three with
+  // 8192 entries + distinct[8192] + {min, max, lo, shift, flag}
+  const size_t meta_bytes = align_up(sizeof(uint32_t) * (size_t)std::max(3 * P, 4 * kBkParts + 64), 256);
   const size_t keys_bytes = align_up(sizeof(uint32_t) * (size_t)(m + 64), 256);
   const size_t rle_bytes = align_up(sizeof(uint64_t) * (size_t)(m + 2), 256);
   const size_t heads_bytes = align_up(sizeof(uint32_t) * (size_t)((m + kRleTile - 1) / kRleTile + 1), 256);
@@ -1347,6 +1350,8 @@ static int launch_runs_insert(nvtb_hashagg* h, const int32_t* kp, const uint8_t*
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
     NVTB_CUDA_OK(cudaFuncSetAttribute(merge_write_kernel<false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
+    NVTB_CUDA_OK(cudaFuncSetAttribute(merge_write_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
     attrs = true;
   }
   const int64_t ua = h->u_known;
@@ -1362,40 +1367,108 @@ static int launch_runs_insert(nvtb_hashagg* h, const int32_t* kp, const uint8_t*
   const int aligned = is_aligned32(kp) ? 1 : 0;
   uint32_t* n_valid = h->d_n + 1;
   uint32_t* n_batch = h->d_n + 2;
-  // (1) LSD radix sort of the valid keys (as key ^ 2^31)
-  NVTB_CUDA_OK(cudaMemsetAsync(c.part_meta, 0, sizeof(uint32_t) * P, st));
   const int64_t tiles = (m + kPartTile - 1) / kPartTile;
-  part_hist_kernel<PartKeyLow><<<(int)std::min<int64_t>(tiles, 3 * sms), kPartThreads, 4 * P, st>>>(
-      kp, mp, m, PartKeyLow{kSortLowBits}, c.part_meta, h->ctr, aligned);
-  NVTB_LAUNCH_OK();
-  part_scan_kernel<<<1, kPartThreads, 0, st>>>(c.part_meta, kSortLowBits, c.part_meta + P, c.part_meta + 2 * P, 1u, n_valid);
-  NVTB_LAUNCH_OK();
-  part_scatter_kernel<PartKeyLow><<<(int)std::min<int64_t>(tiles, 2 * sms), kPartThreads, kScatterSmem, st>>>(
-      kp, mp, m, PartKeyLow{kSortLowBits}, c.part_meta + 2 * P, reinterpret_cast<int32_t*>(c.keys_a), aligned);
-  NVTB_LAUNCH_OK();
-  int in_b = 0;
-  rc = rx_sort_bits<uint32_t>(c.keys_a, c.keys_b, n_valid, m, kSortLowBits, 32, false, c.rx, st, &in_b);
-  if (rc) return rc;
-  const uint32_t* sorted = in_b ? c.keys_b : c.keys_a;
-  // (2) run heads
-  const int rt = (int)((m + kRleTile - 1) / kRleTile);
-  rle_count_kernel<<<rt, kRunThreads, 0, st>>>(sorted, n_valid, m, c.tile_heads);
-  NVTB_LAUNCH_OK();
-  scan_tiles_kernel<<<1, kRunThreads, 0, st>>>(c.tile_heads, rt, n_batch, nullptr);
-  NVTB_LAUNCH_OK();
-  rle_write_kernel<<<rt, kRunThreads, 0, st>>>(sorted, n_valid, m, c.tile_heads, n_batch, c.rle);
-  NVTB_LAUNCH_OK();
-  // (3) merge with the accumulator
   const uint64_t* A = h->acc[h->acc_cur];
-  merge_split_kernel<<<(int)((mt + 1 + 255) / 256), 256, 0, st>>>(A, (uint32_t)ua, c.rle, n_batch, (int)mt, c.splits);
-  NVTB_LAUNCH_OK();
-  merge_count_kernel<<<(int)mt, kRunThreads, 0, st>>>(A, c.rle, c.splits, c.tile_out);
-  NVTB_LAUNCH_OK();
-  scan_tiles_kernel<<<1, kRunThreads, 0, st>>>(c.tile_out, (int)mt, nullptr, &h->ctr->n_unique);
-  NVTB_LAUNCH_OK();
-  merge_write_kernel<false><<<(int)mt, kRunThreads, sizeof(MergeSmem), st>>>(A, c.rle, c.splits, c.tile_out, h->acc[other],
-                                                                     &h->ctr->max_count);
-  NVTB_LAUNCH_OK();
+  // ---- bucket path (bucketagg.cuh): range partition + direct-address counting, no sort ----------
+  bool done = false;
+  const char* path_env = getenv("NVTB_SORT_PATH");
+  if (!(path_env && strcmp(path_env, "radix") == 0)) {
+    static bool bk_attrs = false;
+    constexpr int kBkScatterSmem = kPartTile * 4 + 2 * 4 * kBkParts;
+    if (!bk_attrs) {
+      NVTB_CUDA_OK(cudaFuncSetAttribute(part_hist_kernel<PartRange>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kBkParts));
+      NVTB_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<PartRange>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBkScatterSmem));
+      NVTB_CUDA_OK(cudaFuncSetAttribute(bk_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBkCountSmem));
+      NVTB_CUDA_OK(cudaFuncSetAttribute(bk_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBkEmitSmem));
+      bk_attrs = true;
+    }
+    uint32_t* total = c.part_meta;                    // -> exclusive starts after the scan
+    uint32_t* cursor = c.part_meta + kBkParts;
+    uint32_t* distinct = c.part_meta + 2 * kBkParts;  // -> output offsets after the scan
+    uint32_t* mm = c.part_meta + 4 * kBkParts;        // {min, max}
+    uint32_t* par = mm + 2;                           // {lo, shift}
+    unsigned int* flag = reinterpret_cast<unsigned int*>(mm + 4);
+    const uint32_t mm_init[6] = {0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};
+    NVTB_CUDA_OK(cudaMemcpyAsync(mm, mm_init, sizeof(mm_init), cudaMemcpyHostToDevice, st));
+    NVTB_CUDA_OK(cudaMemsetAsync(total, 0, sizeof(uint32_t) * kBkParts, st));
+    bk_minmax_kernel<<<(int)std::min<int64_t>(tiles, 4 * sms), kPartThreads, 0, st>>>(kp, mp, m, mm, aligned);
+    NVTB_LAUNCH_OK();
+    bk_params_kernel<<<1, 1, 0, st>>>(mm, par);
+    NVTB_LAUNCH_OK();
+    const PartRange pol{kBkLgParts, par};
+    part_hist_kernel<PartRange><<<(int)std::min<int64_t>(tiles, 3 * sms), kPartThreads, 4 * kBkParts, st>>>(
+        kp, mp, m, pol, total, h->ctr, aligned);
+    NVTB_LAUNCH_OK();
+    scan_tiles_kernel<<<1, kRunThreads, 0, st>>>(total, kBkParts, n_valid, nullptr);
+    NVTB_LAUNCH_OK();
+    NVTB_CUDA_OK(cudaMemcpyAsync(cursor, total, sizeof(uint32_t) * kBkParts, cudaMemcpyDeviceToDevice, st));
+    part_scatter_kernel<PartRange><<<(int)std::min<int64_t>(tiles, sms), kPartThreads, kBkScatterSmem, st>>>(
+        kp, mp, m, pol, cursor, reinterpret_cast<int32_t*>(c.keys_a), aligned);
+    NVTB_LAUNCH_OK();
+    bk_count_kernel<<<kBkParts, kBkThreads, kBkCountSmem, st>>>(c.keys_a, total, n_valid, par, distinct);
+    NVTB_LAUNCH_OK();
+    // the batch's pairs go straight into the accumulator when it is empty, else to the merge input
+    uint64_t* B = (ua == 0) ? h->acc[other] : c.rle;
+    scan_tiles_kernel<<<1, kRunThreads, 0, st>>>(distinct, kBkParts, n_batch, ua == 0 ? &h->ctr->n_unique : nullptr);
+    NVTB_LAUNCH_OK();
+    bk_emit_kernel<<<kBkParts, kBkThreads, kBkEmitSmem, st>>>(c.keys_a, total, n_valid, par, distinct, B, flag,
+                                                               &h->ctr->max_count);
+    NVTB_LAUNCH_OK();
+    unsigned int flag_h = 0;
+    NVTB_CUDA_OK(cudaMemcpyAsync(&flag_h, flag, sizeof(flag_h), cudaMemcpyDeviceToHost, st));
+    NVTB_CUDA_OK(cudaStreamSynchronize(st));
+    if (flag_h == 0) {
+      if (ua > 0) {
+        merge_split_kernel<<<(int)((mt + 1 + 255) / 256), 256, 0, st>>>(A, (uint32_t)ua, B, n_batch, (int)mt, c.splits);
+        NVTB_LAUNCH_OK();
+        merge_count_kernel<<<(int)mt, kRunThreads, 0, st>>>(A, B, c.splits, c.tile_out);
+        NVTB_LAUNCH_OK();
+        scan_tiles_kernel<<<1, kRunThreads, 0, st>>>(c.tile_out, (int)mt, nullptr, &h->ctr->n_unique);
+        NVTB_LAUNCH_OK();
+        merge_write_kernel<true><<<(int)mt, kRunThreads, sizeof(MergeSmem), st>>>(A, B, c.splits, c.tile_out, h->acc[other],
+                                                                                  &h->ctr->max_count);
+        NVTB_LAUNCH_OK();
+      }
+      done = true;
+    }
+    // flag set: some window holds more than kBkDupCap duplicated values -> the radix pipeline
+    // below redoes the batch (the nulls have been counted already)
+  }
+  if (!done) {
+    Counters* null_ctr = (path_env && strcmp(path_env, "radix") == 0) ? h->ctr : nullptr;
+    // (1) LSD radix sort of the valid keys (as key ^ 2^31)
+    NVTB_CUDA_OK(cudaMemsetAsync(c.part_meta, 0, sizeof(uint32_t) * P, st));
+    part_hist_kernel<PartKeyLow><<<(int)std::min<int64_t>(tiles, 3 * sms), kPartThreads, 4 * P, st>>>(
+        kp, mp, m, PartKeyLow{kSortLowBits}, c.part_meta, null_ctr, aligned);
+    NVTB_LAUNCH_OK();
+    part_scan_kernel<<<1, kPartThreads, 0, st>>>(c.part_meta, kSortLowBits, c.part_meta + P, c.part_meta + 2 * P, 1u, n_valid);
+    NVTB_LAUNCH_OK();
+    part_scatter_kernel<PartKeyLow><<<(int)std::min<int64_t>(tiles, 2 * sms), kPartThreads, kScatterSmem, st>>>(
+        kp, mp, m, PartKeyLow{kSortLowBits}, c.part_meta + 2 * P, reinterpret_cast<int32_t*>(c.keys_a), aligned);
+    NVTB_LAUNCH_OK();
+    int in_b = 0;
+    rc = rx_sort_bits<uint32_t>(c.keys_a, c.keys_b, n_valid, m, kSortLowBits, 32, false, c.rx, st, &in_b);
+    if (rc) return rc;
+    const uint32_t* sorted = in_b ? c.keys_b : c.keys_a;
+    // (2) run heads
+    const int rt = (int)((m + kRleTile - 1) / kRleTile);
+    rle_count_kernel<<<rt, kRunThreads, 0, st>>>(sorted, n_valid, m, c.tile_heads);
+    NVTB_LAUNCH_OK();
+    scan_tiles_kernel<<<1, kRunThreads, 0, st>>>(c.tile_heads, rt, n_batch, nullptr);
+    NVTB_LAUNCH_OK();
+    rle_write_kernel<<<rt, kRunThreads, 0, st>>>(sorted, n_valid, m, c.tile_heads, n_batch, c.rle);
+    NVTB_LAUNCH_OK();
+    // (3) merge with the accumulator
+    merge_split_kernel<<<(int)((mt + 1 + 255) / 256), 256, 0, st>>>(A, (uint32_t)ua, c.rle, n_batch, (int)mt, c.splits);
+    NVTB_LAUNCH_OK();
+    merge_count_kernel<<<(int)mt, kRunThreads, 0, st>>>(A, c.rle, c.splits, c.tile_out);
+    NVTB_LAUNCH_OK();
+    scan_tiles_kernel<<<1, kRunThreads, 0, st>>>(c.tile_out, (int)mt, nullptr, &h->ctr->n_unique);
+    NVTB_LAUNCH_OK();
+    merge_write_kernel<false><<<(int)mt, kRunThreads, sizeof(MergeSmem), st>>>(A, c.rle, c.splits, c.tile_out, h->acc[other],
+                                                                               &h->ctr->max_count);
+    NVTB_LAUNCH_OK();
+  }
   h->acc_cur = other;
   return sort_scratch_release(st);
 }

@@ -39,6 +39,22 @@ namespace nvtb {
 //   narrow ( 8 B) ((uint32)(position + 1) << 32) | (uint32)key; empty = 0.  Used when
 //                 every key fits int32 and n < 2^31: half the footprint, so more of
 //                 the table stays in L1/L2, and one 8-byte load per probe.
+// Narrow (int32-key) tables probe WITHIN a slice of the table: bucket b is followed by the next
+// bucket of the same slice, wrapping at the slice end.  A slice is 8192 buckets (256 KB) — more
+// when the table has more than 8192 slices — so that one CTA can build a whole slice while it
+// stays in the L2 (slice_build_kernel), and no probe sequence ever leaves the CTA's slice.
+constexpr int64_t kSliceBuckets = 8192;
+constexpr int kSliceParts = 8192;                 // at most this many slices
+__host__ __device__ __forceinline__ int64_t narrow_slice_buckets(int64_t nbuckets) {
+  int64_t s = nbuckets / kSliceParts;
+  if (s < kSliceBuckets) s = kSliceBuckets;
+  return s < nbuckets ? s : nbuckets;             // powers of two throughout
+}
+__host__ __device__ __forceinline__ int64_t narrow_next(int64_t b, int64_t nbuckets) {
+  const int64_t sm = narrow_slice_buckets(nbuckets) - 1;
+  return (b & ~sm) | ((b + 1) & sm);
+}
+
 struct Lookup {
   int64_t* slots;     // wide: [2*capacity]; narrow: [capacity]
   int64_t capacity;   // power of two, >= 2 * n
@@ -170,7 +186,7 @@ __device__ __forceinline__ int64_t lookup_resolve(const Lookup& t, int64_t key, 
       if (p.k == key) { pos = p.v; done = true; }
       else if (p.k == kEmptyKey) done = true;
     }
-    if (!done) lookup_load<NARROW>(t, (p.b + 1) & mask, p);
+    if (!done) lookup_load<NARROW>(t, NARROW ? narrow_next(p.b, mask + 1) : ((p.b + 1) & mask), p);
   }
   return pos;
 }
@@ -506,7 +522,126 @@ lookup_build_packed_kernel(const uint64_t* __restrict__ p, int64_t n, unsigned l
     bool placed = false;
     while (!placed) {
       for (int j = 0; j < 4 && !placed; ++j) placed = (atomicCAS(slots + 4 * b + j, 0ull, want) == 0ull);
-      b = (b + 1) & bmask;
+      b = narrow_next(b, bmask + 1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// slice-wise build of a large narrow lookup.  One random insert per key into a multi-GB table is
+// one DRAM-resident atomic per key (10 ms per 1.7e8 keys: 22 % of the DRAM peak, every warp
+// waiting on its CAS).  Instead the (position, key) items are partitioned by the table slice
+// their home bucket lies in (order-free: shared-memory counts, one reservation per tile and
+// slice), and one CTA then zero-fills and fills ITS slice: the slice stays in the L2 while it
+// is built, the atomics are L2 hits, and every table line reaches HBM exactly once.
+// ---------------------------------------------------------------------------------------
+constexpr int kSlThreads = 512;
+constexpr int kSlTile = 8192;                      // items per tile of the scatter (64 KB staged)
+
+__device__ __forceinline__ uint32_t slice_of(uint32_t key, uint32_t bmask, int lg_slice) {
+  return (table_mix32(key) & bmask) >> lg_slice;
+}
+
+static __global__ void __launch_bounds__(kSlThreads)
+slice_hist_kernel(const uint64_t* __restrict__ p, int64_t n, uint32_t bmask, int lg_slice, int P,
+                  uint32_t* __restrict__ total) {
+  extern __shared__ __align__(16) uint32_t sl_smem[];
+  uint32_t* cnt = sl_smem;
+  for (int d = threadIdx.x; d < P; d += kSlThreads) cnt[d] = 0u;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * kSlThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kSlThreads + threadIdx.x; i < n; i += stride)
+    atomicAdd(&cnt[slice_of((uint32_t)(p[i] >> 32) ^ 0x80000000u, bmask, lg_slice)], 1u);
+  __syncthreads();
+  for (int d = threadIdx.x; d < P; d += kSlThreads)
+    if (cnt[d]) atomicAdd(&total[d], cnt[d]);
+}
+
+// total[P] -> starts[P + 1] (exclusive) and cursor[P]
+static __global__ void __launch_bounds__(kSlThreads)
+slice_scan_kernel(const uint32_t* __restrict__ total, int P, uint32_t* __restrict__ starts, uint32_t* __restrict__ cursor) {
+  extern __shared__ __align__(16) uint32_t sl_smem[];
+  __shared__ uint32_t ws[kSlThreads / 32 + 1];
+  uint32_t* v = sl_smem;
+  uint32_t* o = sl_smem + P;
+  for (int d = threadIdx.x; d < P; d += kSlThreads) v[d] = total[d];
+  __syncthreads();
+  const uint32_t tot = rx_block_excl_scan<kSlThreads>(v, o, P, ws);
+  for (int d = threadIdx.x; d < P; d += kSlThreads) { starts[d] = o[d]; cursor[d] = o[d]; }
+  if (threadIdx.x == 0) starts[P] = tot;
+}
+
+// items[...] = ((pos + 1) << 32) | key, grouped by slice
+static __global__ void __launch_bounds__(kSlThreads)
+slice_scatter_kernel(const uint64_t* __restrict__ p, int64_t n, uint32_t bmask, int lg_slice, int P,
+                     uint32_t* __restrict__ cursor, uint64_t* __restrict__ items) {
+  extern __shared__ __align__(16) unsigned char sl_raw[];
+  uint64_t* stage = reinterpret_cast<uint64_t*>(sl_raw);                        // [kSlTile]
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(stage + kSlTile);                 // [P]
+  uint32_t* delta = cnt + P;                                                    // [P]
+  __shared__ uint32_t ws[kSlThreads / 32 + 1];
+  constexpr int kPer = kSlTile / kSlThreads;                                    // 16 items per thread
+  const int64_t n_tiles = (n + kSlTile - 1) / kSlTile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int d = threadIdx.x; d < P; d += kSlThreads) cnt[d] = 0u;
+    __syncthreads();
+    uint32_t key[kPer];
+    uint16_t bin[kPer];
+    const int64_t base = tile * kSlTile;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int64_t i = base + (int64_t)j * kSlThreads + threadIdx.x;
+      key[j] = i < n ? ((uint32_t)(p[i] >> 32) ^ 0x80000000u) : 0u;
+      bin[j] = (uint16_t)slice_of(key[j], bmask, lg_slice);
+      if (i < n) atomicAdd(&cnt[bin[j]], 1u);
+    }
+    __syncthreads();
+    const uint32_t total = rx_block_excl_scan<kSlThreads>(cnt, delta, P, ws);   // staged offsets
+    for (int d = threadIdx.x; d < P; d += kSlThreads) {
+      const uint32_t c = cnt[d], off = delta[d];
+      uint32_t g0 = 0;
+      if (c) g0 = atomicAdd(&cursor[d], c);
+      delta[d] = g0 - off;            // global index = delta + staged index (mod 2^32)
+      cnt[d] = off;                   // running staged cursor
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int64_t i = base + (int64_t)j * kSlThreads + threadIdx.x;
+      if (i < n) {
+        const uint32_t q = atomicAdd(&cnt[bin[j]], 1u);
+        stage[q] = ((uint64_t)(uint32_t)(i + 1) << 32) | key[j];
+      }
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < total; j += kSlThreads) {
+      const uint64_t it = stage[j];
+      items[delta[slice_of((uint32_t)it, bmask, lg_slice)] + j] = it;
+    }
+    __syncthreads();
+  }
+}
+
+// one CTA per slice: zero-fill, then claim the first free slot of the home bucket (or of the
+// following buckets of the SAME slice)
+static __global__ void __launch_bounds__(1024)
+slice_build_kernel(const uint64_t* __restrict__ items, const uint32_t* __restrict__ starts,
+                   unsigned long long* __restrict__ slots, uint32_t bmask, int lg_slice) {
+  const int sl = blockIdx.x;
+  const int64_t slice_buckets = (int64_t)1 << lg_slice;
+  unsigned long long* base = slots + (int64_t)sl * slice_buckets * 4;
+  ulonglong2* z = reinterpret_cast<ulonglong2*>(base);
+  for (int64_t i = threadIdx.x; i < slice_buckets * 2; i += blockDim.x) z[i] = make_ulonglong2(0ull, 0ull);
+  __syncthreads();
+  const uint32_t s = starts[sl], e = starts[sl + 1];
+  const int64_t sm = slice_buckets - 1;
+  for (uint32_t i = s + threadIdx.x; i < e; i += blockDim.x) {
+    const unsigned long long want = items[i];
+    int64_t b = (int64_t)(table_mix32((uint32_t)want) & bmask) & sm;     // bucket inside the slice
+    bool placed = false;
+    while (!placed) {
+      for (int j = 0; j < 4 && !placed; ++j) placed = (atomicCAS(base + 4 * b + j, 0ull, want) == 0ull);
+      b = (b + 1) & sm;
     }
   }
 }
@@ -619,7 +754,7 @@ lookup_build_any_kernel(const int64_t* __restrict__ keys, int64_t n, int64_t* sl
       bool placed = false;
       while (!placed) {
         for (int j = 0; j < 4 && !placed; ++j) placed = (atomicCAS(ns + 4 * b + j, 0ull, want) == 0ull);
-        b = (b + 1) & bmask;
+        b = narrow_next(b, bmask + 1);
       }
     } else {
       if (k == kEmptyKey) { *min_key_pos = i; continue; }
@@ -744,7 +879,7 @@ small_vocab_kernel(const int64_t* __restrict__ keys_in, const int64_t* __restric
       bool placed = false;
       while (!placed) {                                   // keys are distinct
         for (int j = 0; j < 4 && !placed; ++j) placed = (atomicCAS(ns + 4 * b + j, 0ull, want) == 0ull);
-        b = (b + 1) & bmask;
+        b = narrow_next(b, bmask + 1);
       }
     } else if (key == kEmptyKey) {
       min_pos = i;
@@ -1106,12 +1241,49 @@ static int finish_packed_vocab(nvtb_vocab* v, uint64_t* sorted, int64_t n, int64
   v->t.min_key_pos = -1;
   v->t.narrow = 1;
   NVTB_CUDA_OK(cudaMallocAsync(&v->t.slots, sizeof(int64_t) * v->t.capacity, st));
-  NVTB_CUDA_OK(cudaMemsetAsync(v->t.slots, 0, sizeof(int64_t) * v->t.capacity, st));
+  const int64_t nbuckets = v->t.capacity >> 2;
+  const int64_t slice_buckets = narrow_slice_buckets(nbuckets);
+  const int64_t n_slices = nbuckets / slice_buckets;
+  const bool sliced = n_keep >= ((int64_t)1 << 20) && n_slices >= kSlThreads && n_keep < (int64_t)0xFFFFFFF0ll &&
+                      !(getenv("NVTB_LOOKUP_BUILD") && strcmp(getenv("NVTB_LOOKUP_BUILD"), "atomic") == 0);
+  if (!sliced) NVTB_CUDA_OK(cudaMemsetAsync(v->t.slots, 0, sizeof(int64_t) * v->t.capacity, st));
   if (n_keep > 0) {
     const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>((n_keep + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
-    lookup_build_packed_kernel<<<g1, kThreads, 0, st>>>(sorted, n_keep, reinterpret_cast<unsigned long long*>(v->t.slots),
-                                                        v->t.capacity);
-    NVTB_LAUNCH_OK();
+    if (sliced) {
+      static bool sl_attrs = false;
+      const int P = (int)n_slices;                                   // a power of two <= 8192
+      int lg_slice = 0;
+      while (((int64_t)1 << lg_slice) < slice_buckets) ++lg_slice;
+      const int scatter_smem = kSlTile * 8 + 2 * 4 * kSliceParts;
+      if (!sl_attrs) {
+        NVTB_CUDA_OK(cudaFuncSetAttribute(slice_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * kSliceParts));
+        NVTB_CUDA_OK(cudaFuncSetAttribute(slice_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_smem));
+        sl_attrs = true;
+      }
+      uint32_t* meta = nullptr;                                      // total[P] | starts[P + 1] | cursor[P]
+      uint64_t* items = nullptr;
+      NVTB_CUDA_OK(cudaMallocAsync(&meta, sizeof(uint32_t) * (3 * (size_t)P + 8), st));
+      NVTB_CUDA_OK(cudaMallocAsync(&items, sizeof(uint64_t) * (size_t)n_keep, st));
+      NVTB_CUDA_OK(cudaMemsetAsync(meta, 0, sizeof(uint32_t) * P, st));
+      const uint32_t bmask = (uint32_t)(nbuckets - 1);
+      const int sms = sm_count();
+      slice_hist_kernel<<<4 * sms, kSlThreads, 4 * P, st>>>(sorted, n_keep, bmask, lg_slice, P, meta);
+      NVTB_LAUNCH_OK();
+      slice_scan_kernel<<<1, kSlThreads, 2 * 4 * P, st>>>(meta, P, meta + P, meta + 2 * P + 1);
+      NVTB_LAUNCH_OK();
+      const int64_t tiles = (n_keep + kSlTile - 1) / kSlTile;
+      slice_scatter_kernel<<<(int)std::min<int64_t>(tiles, sms), kSlThreads, kSlTile * 8 + 2 * 4 * P, st>>>(
+          sorted, n_keep, bmask, lg_slice, P, meta + 2 * P + 1, items);
+      NVTB_LAUNCH_OK();
+      slice_build_kernel<<<P, 1024, 0, st>>>(items, meta + P, reinterpret_cast<unsigned long long*>(v->t.slots), bmask, lg_slice);
+      NVTB_LAUNCH_OK();
+      NVTB_CUDA_OK(cudaFreeAsync(items, st));
+      NVTB_CUDA_OK(cudaFreeAsync(meta, st));
+    } else {
+      lookup_build_packed_kernel<<<g1, kThreads, 0, st>>>(sorted, n_keep, reinterpret_cast<unsigned long long*>(v->t.slots),
+                                                          v->t.capacity);
+      NVTB_LAUNCH_OK();
+    }
     if (n_keep <= kEncSmemMaxKeys) {        // the shared-memory encode reads int64 keys
       NVTB_CUDA_OK(cudaMallocAsync(&v->keys, sizeof(int64_t) * n_keep, st));
       packed_unpack_kernel<<<g1, kThreads, 0, st>>>(sorted, n_keep, v->keys, nullptr);

@@ -175,3 +175,59 @@ def test_vocab_from_sorted_accumulator(monkeypatch, cut):
     exp = torch.where(hit, perm[idx] + 3, torch.full_like(idx, 2))
     exp = torch.where(valid, exp, torch.ones_like(exp))
     assert torch.equal(labels, exp)
+
+
+@pytest.mark.parametrize("shape", ["uniform32", "dense_small_range", "heavy_hitters", "cluster_fallback"])
+def test_bucket_groupby_paths_agree(monkeypatch, shape):
+    """The staged batches of a sorted accumulator are grouped by ONE range partition + direct-address
+    counting in shared memory (csrc/bucketagg.cuh); the radix pipeline (NVTB_SORT_PATH=radix) is the
+    fallback when a window holds more duplicated values than the counters a CTA has.  Both must give
+    torch.unique's answer for: keys over the whole int32 range; a dense small range (the window
+    shrinks to a few values); a few values with millions of rows each; and a dense cluster inside a
+    wide range (more than 14 336 duplicated values in one 2^18 window: the fallback fires)."""
+    engine, Column, pack_validity = _engine()
+    monkeypatch.setenv("NVTB_RUNS_MIN_KEYS", "1")
+    n = 4_000_000
+    g = torch.Generator(device="cuda").manual_seed(len(shape))
+    if shape == "uniform32":
+        keys = torch.randint(-2**31, 2**31 - 1, (n,), generator=g, device="cuda", dtype=torch.int64)
+    elif shape == "dense_small_range":
+        keys = torch.randint(-500, 70_000, (n,), generator=g, device="cuda", dtype=torch.int64)
+    elif shape == "heavy_hitters":
+        keys = torch.randint(-2**31, 2**31 - 1, (n,), generator=g, device="cuda", dtype=torch.int64)
+        hot = torch.rand(n, generator=g, device="cuda") < 0.6
+        keys = torch.where(hot, torch.randint(0, 5, (n,), generator=g, device="cuda", dtype=torch.int64) * 123_456_789, keys)
+    else:
+        wide = torch.randint(-2**31, 2**31 - 1, (n,), generator=g, device="cuda", dtype=torch.int64)
+        dense = 1_000 + torch.randint(0, 100_000, (n,), generator=g, device="cuda", dtype=torch.int64)
+        keys = torch.where(torch.rand(n, generator=g, device="cuda") < 0.5, dense, wide)
+    keys = keys.to(torch.int32)
+    valid = torch.rand(n, generator=g, device="cuda") > 0.02
+    u, c = _ref_counts(keys, valid)
+    cuts = [0, 64 * 11000, 64 * 30000, n]
+    for path in ("", "radix"):
+        if path:
+            monkeypatch.setenv("NVTB_SORT_PATH", path)
+        else:
+            monkeypatch.delenv("NVTB_SORT_PATH", raising=False)
+        agg = _insert_batches(engine, Column, pack_validity, keys, valid, cuts)
+        assert agg.mode == 1
+        k, s, _, null_size, _ = agg.export()
+        assert torch.equal(k, u) and torch.equal(s, c), (shape, path)
+        assert null_size == int((~valid).sum())
+
+
+def test_small_staging_buffer_merges_flushes(monkeypatch):
+    """NVTB_STAGE_ROWS below the fit size: several flushes, each merged into the accumulator"""
+    engine, Column, pack_validity = _engine()
+    monkeypatch.setenv("NVTB_RUNS_MIN_KEYS", "1")
+    monkeypatch.setenv("NVTB_STAGE_ROWS", str(64 * 9000))
+    n = 3_000_000
+    g = torch.Generator(device="cuda").manual_seed(77)
+    keys = (torch.randint(0, 900_000, (n,), generator=g, device="cuda", dtype=torch.int64) * 2654435761 % (2**32) - 2**31).to(torch.int32)
+    valid = torch.rand(n, generator=g, device="cuda") > 0.05
+    cuts = list(range(0, n, 64 * 5000)) + [n]
+    agg = _insert_batches(engine, Column, pack_validity, keys, valid, cuts)
+    k, s, _, null_size, _ = agg.export()
+    u, c = _ref_counts(keys, valid)
+    assert torch.equal(k, u) and torch.equal(s, c) and null_size == int((~valid).sum())
