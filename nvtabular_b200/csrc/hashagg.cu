@@ -1356,8 +1356,7 @@ static int launch_runs_insert(nvtb_hashagg* h, const int32_t* kp, const uint8_t*
   }
   const int64_t ua = h->u_known;
   const int other = h->acc_cur ^ 1;
-  int rc = acc_reserve(h, other, ua + m, st);
-  if (rc) return rc;
+  int rc = NVTB_OK;
   const int64_t mt = (ua + m + kMergeTile - 1) / kMergeTile;
   SortCarve c;
   rc = sort_scratch_acquire(m, 64, mt, st, &c);
@@ -1407,10 +1406,17 @@ static int launch_runs_insert(nvtb_hashagg* h, const int32_t* kp, const uint8_t*
     NVTB_LAUNCH_OK();
     bk_count_kernel<<<kBkParts, kBkThreads, kBkCountSmem, st>>>(c.keys_a, total, n_valid, par, distinct);
     NVTB_LAUNCH_OK();
-    // the batch's pairs go straight into the accumulator when it is empty, else to the merge input
-    uint64_t* B = (ua == 0) ? h->acc[other] : c.rle;
     scan_tiles_kernel<<<1, kRunThreads, 0, st>>>(distinct, kBkParts, n_batch, ua == 0 ? &h->ctr->n_unique : nullptr);
     NVTB_LAUNCH_OK();
+    // the accumulator is sized for what the batch really holds (its distinct keys are known now),
+    // not for the worst case of all rows distinct: 1.3 GB instead of 2.2 GB per buffer at 2.5e8 rows
+    uint32_t nb_h = 0;
+    NVTB_CUDA_OK(cudaMemcpyAsync(&nb_h, n_batch, sizeof(nb_h), cudaMemcpyDeviceToHost, st));
+    NVTB_CUDA_OK(cudaStreamSynchronize(st));
+    rc = acc_reserve(h, other, ua + (int64_t)nb_h, st);
+    if (rc) return rc;
+    // the batch's pairs go straight into the accumulator when it is empty, else to the merge input
+    uint64_t* B = (ua == 0) ? h->acc[other] : c.rle;
     bk_emit_kernel<<<kBkParts, kBkThreads, kBkEmitSmem, st>>>(c.keys_a, total, n_valid, par, distinct, B, flag,
                                                                &h->ctr->max_count);
     NVTB_LAUNCH_OK();
@@ -1435,6 +1441,8 @@ static int launch_runs_insert(nvtb_hashagg* h, const int32_t* kp, const uint8_t*
     // below redoes the batch (the nulls have been counted already)
   }
   if (!done) {
+    rc = acc_reserve(h, other, ua + m, st);
+    if (rc) return rc;
     Counters* null_ctr = (path_env && strcmp(path_env, "radix") == 0) ? h->ctr : nullptr;
     // (1) LSD radix sort of the valid keys (as key ^ 2^31)
     NVTB_CUDA_OK(cudaMemsetAsync(c.part_meta, 0, sizeof(uint32_t) * P, st));

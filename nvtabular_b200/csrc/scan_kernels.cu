@@ -16,6 +16,8 @@
 #include <cstdarg>
 #include <limits>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace nvtb {
@@ -56,6 +58,13 @@ void ensure_pool_configured() {
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     unsigned long long keep = ~0ull;   // never trim: the engine re-uses these buffers every batch
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  // NVTB_L2_FETCH=32|64|128: L2 fetch granularity hint.  The lookups of the large vocabularies are
+  // one random 32-byte sector per row; ncu shows 125 B of DRAM reads per row (the L2 fetches whole
+  // 128-byte lines), so a smaller granularity leaves more of the DRAM bandwidth to useful sectors.
+  if (const char* e = getenv("NVTB_L2_FETCH")) {
+    const size_t g = (size_t)atoll(e);
+    if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
   }
   done_dev = dev;
 }

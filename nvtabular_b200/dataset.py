@@ -98,8 +98,15 @@ class Dataset:
         self._source = data
         self._npartitions = npartitions
         if isinstance(data, Dataset):
+            # same source, same partitioning: a Dataset that has not been ingested yet must split
+            # the way its parent would (TargetEncoding draws its folds per partition)
+            if data._parts is None:
+                data._parts = data._ingest()
             self._source = data._source
             self._parts = data._parts
+            self._npartitions = data._npartitions
+            self._part_rows = data._part_rows
+            self._device = data._device
             # a lazily transformed Dataset handed to another Workflow: CHAIN the transforms
             # (wf2.transform(wf1.transform(ds)) runs wf2 on wf1's output, like the reference)
             prev = data._transform

@@ -327,7 +327,7 @@ class Categorify(StatOperator):
         else:
             space = KeySpace("int", None, np.dtype("int64") if values.dtype.itemsize == 8 else np.dtype("int32"))
         keys = torch.from_numpy(space.encode_values(values).astype(np.int64)).cuda()
-        szt = torch.from_numpy(np.asarray(sizes, dtype=np.int64)).cuda() if sizes is not None else None
+        szt = torch.from_numpy(np.array(sizes, dtype=np.int64, copy=True)).cuda() if sizes is not None else None
         vocab = engine.Vocab.from_arrays(keys, szt)
         return FittedVocab(col_name, [col_name], space, vocab, self._nb(col_name),
                            has_sizes=sizes is not None, index_start=index_start)

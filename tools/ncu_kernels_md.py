@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 COLS = [
-    ("us", "gpu__time_duration.sum", lambda v: f"{v / 1e3 if v > 5e3 else v:.0f}"),
+    ("us", "gpu__time_duration.sum", lambda v: f"{v:.0f}"),
     ("DRAM rd MB", "dram__bytes_read.sum", lambda v: f"{v:.0f}"),
     ("DRAM wr MB", "dram__bytes_write.sum", lambda v: f"{v:.0f}"),
     ("DRAM %", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", lambda v: f"{v:.0f}"),
@@ -27,8 +27,16 @@ def num(x):
         return float("nan")
 
 
+_TIME = {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}
+_BYTES = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+
+
 def main(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """path: a .ncu-rep (needs ncu) or the `ncu -i rep --page raw --csv` output saved as .csv"""
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ix = {h: i for i, h in enumerate(hdr)}
@@ -40,8 +48,12 @@ def main(path):
         cells = []
         for _, key, fmt in COLS:
             v = num(r[ix[key]]) if key in ix else float("nan")
-            if key == "gpu__time_duration.sum" and units[ix[key]] in ("ns", "nsecond"):
-                v = v  # ns
+            if key in ix:
+                u = units[ix[key]]
+                if key == "gpu__time_duration.sum":
+                    v = v * _TIME.get(u, 1.0)            # -> us
+                elif key.startswith("dram__bytes"):
+                    v = v * _BYTES.get(u, 1e-6)          # -> MB
             cells.append(fmt(v))
         conf = num(r[ix.get("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", 0)])
         wav = num(r[ix.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", 0)])
