@@ -13,6 +13,7 @@ include/nvtb200.h (nvtabular_b200/lib/libnvtb200.so).
 __version__ = "0.1.0"
 
 from . import ops  # noqa: F401
+from . import serialize  # noqa: F401
 from .column import Column, DeviceFrame  # noqa: F401
 from .dataset import Dataset  # noqa: F401
 from .graph import ColumnSchema, ColumnSelector, Node, Schema, Tags  # noqa: F401

@@ -370,42 +370,54 @@ __device__ __forceinline__ uint64_t hash_one(const HashCols& hc, int c,
   return pandas_mix64(bits);
 }
 
+// h % d without the ~100-instruction software 64-bit division: with M = floor(2^64 / d) (host),
+// q = mulhi(h, M) is the true quotient or one below it, so r = h - q d lies in [0, 2d): one
+// conditional subtraction makes it exact for every d >= 2 (d == 1: M does not fit, result 0).
+__device__ __forceinline__ uint64_t fast_mod_u64(uint64_t h, uint64_t d, uint64_t M) {
+  if (d == 1) return 0;
+  const uint64_t r = h - __umul64hi(h, M) * d;
+  return r >= d ? r - d : r;
+}
+static uint64_t fast_mod_magic(uint64_t d) {
+  return d > 1 ? (uint64_t)((((unsigned __int128)1) << 64) / d) : 0;
+}
+
 // single-column fast path: tiled 256-bit loads
 template <typename T, typename OutT>
 __device__ __forceinline__ void hash_bucket_column(const T* __restrict__ data,
                                                    const uint8_t* __restrict__ mask,
                                                    OutT* __restrict__ out,
-                                                   int64_t n, uint64_t nb,
+                                                   int64_t n, uint64_t nb, uint64_t nb_magic,
                                                    int64_t add) {
   const bool aligned = is_aligned32(data) && is_aligned32(out);
   map_rows<T, OutT>(data, mask, out, n, aligned,
                     [&](int64_t, T x, bool valid) -> OutT {
                       const uint64_t bits = valid ? value_bits<T>(x) : kNaNBits;
-                      return (OutT)((int64_t)(pandas_mix64(bits) % nb) + add);
+                      return (OutT)((int64_t)fast_mod_u64(pandas_mix64(bits), nb, nb_magic) + add);
                     });
 }
 
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads)
 hash_bucket1_kernel(const void* data, const uint8_t* mask, int dtype, OutT* out,
-                    int64_t n, uint64_t nb, int64_t add) {
+                    int64_t n, uint64_t nb, uint64_t nb_magic, int64_t add) {
   switch (dtype) {
-    case NVTB_I32: hash_bucket_column<int32_t, OutT>((const int32_t*)data, mask, out, n, nb, add); break;
-    case NVTB_I64: hash_bucket_column<int64_t, OutT>((const int64_t*)data, mask, out, n, nb, add); break;
-    case NVTB_F32: hash_bucket_column<float, OutT>((const float*)data, mask, out, n, nb, add); break;
-    default:       hash_bucket_column<double, OutT>((const double*)data, mask, out, n, nb, add); break;
+    case NVTB_I32: hash_bucket_column<int32_t, OutT>((const int32_t*)data, mask, out, n, nb, nb_magic, add); break;
+    case NVTB_I64: hash_bucket_column<int64_t, OutT>((const int64_t*)data, mask, out, n, nb, nb_magic, add); break;
+    case NVTB_F32: hash_bucket_column<float, OutT>((const float*)data, mask, out, n, nb, nb_magic, add); break;
+    default:       hash_bucket_column<double, OutT>((const double*)data, mask, out, n, nb, nb_magic, add); break;
   }
 }
 
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads)
-hash_bucketN_kernel(HashCols hc, OutT* __restrict__ out, int64_t n, uint64_t nb,
+hash_bucketN_kernel(HashCols hc, OutT* __restrict__ out, int64_t n, uint64_t nb, uint64_t nb_magic,
                     int64_t add) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     uint64_t h = 0;
     for (int c = 0; c < hc.ncols; ++c) h ^= hash_one(hc, c, i);
-    out[i] = (OutT)((int64_t)(h % nb) + add);
+    out[i] = (OutT)((int64_t)fast_mod_u64(h, nb, nb_magic) + add);
   }
 }
 
@@ -600,13 +612,14 @@ int nvtb_hash_bucket_apply(const nvtb_col_t* cols, int ncols, int64_t n,
   NVTB_REQUIRE(out != nullptr, "out is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = scan_grid(n, 8);
+  const uint64_t magic = fast_mod_magic(num_buckets);
   if (ncols == 1 && cols[0].dtype <= NVTB_F64) {
     if (out_dtype == NVTB_I32)
       hash_bucket1_kernel<int32_t><<<grid, kThreads, 0, st>>>(
-          cols[0].data, cols[0].validity, cols[0].dtype, (int32_t*)out, n, num_buckets, add);
+          cols[0].data, cols[0].validity, cols[0].dtype, (int32_t*)out, n, num_buckets, magic, add);
     else
       hash_bucket1_kernel<int64_t><<<grid, kThreads, 0, st>>>(
-          cols[0].data, cols[0].validity, cols[0].dtype, (int64_t*)out, n, num_buckets, add);
+          cols[0].data, cols[0].validity, cols[0].dtype, (int64_t*)out, n, num_buckets, magic, add);
   } else {
     HashCols hc;
     memset(&hc, 0, sizeof(hc));
@@ -615,9 +628,9 @@ int nvtb_hash_bucket_apply(const nvtb_col_t* cols, int ncols, int64_t n,
       hc.data[c] = cols[c].data; hc.mask[c] = cols[c].validity; hc.dtype[c] = cols[c].dtype;
     }
     if (out_dtype == NVTB_I32)
-      hash_bucketN_kernel<int32_t><<<grid, kThreads, 0, st>>>(hc, (int32_t*)out, n, num_buckets, add);
+      hash_bucketN_kernel<int32_t><<<grid, kThreads, 0, st>>>(hc, (int32_t*)out, n, num_buckets, magic, add);
     else
-      hash_bucketN_kernel<int64_t><<<grid, kThreads, 0, st>>>(hc, (int64_t*)out, n, num_buckets, add);
+      hash_bucketN_kernel<int64_t><<<grid, kThreads, 0, st>>>(hc, (int64_t*)out, n, num_buckets, magic, add);
   }
   NVTB_LAUNCH_OK();
   return NVTB_OK;

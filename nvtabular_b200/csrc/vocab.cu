@@ -536,7 +536,7 @@ lookup_build_packed_kernel(const uint64_t* __restrict__ p, int64_t n, unsigned l
 // is built, the atomics are L2 hits, and every table line reaches HBM exactly once.
 // ---------------------------------------------------------------------------------------
 constexpr int kSlThreads = 512;
-constexpr int kSlTile = 8192;                      // items per tile of the scatter (64 KB staged)
+constexpr int kSlTile = 4096;                      // items per tile of the scatter (32 KB staged): 2 CTAs per SM
 
 __device__ __forceinline__ uint32_t slice_of(uint32_t key, uint32_t bmask, int lg_slice) {
   return (table_mix32(key) & bmask) >> lg_slice;
@@ -572,7 +572,7 @@ slice_scan_kernel(const uint32_t* __restrict__ total, int P, uint32_t* __restric
 }
 
 // items[...] = ((pos + 1) << 32) | key, grouped by slice
-static __global__ void __launch_bounds__(kSlThreads)
+static __global__ void __launch_bounds__(kSlThreads, 2)
 slice_scatter_kernel(const uint64_t* __restrict__ p, int64_t n, uint32_t bmask, int lg_slice, int P,
                      uint32_t* __restrict__ cursor, uint64_t* __restrict__ items) {
   extern __shared__ __align__(16) unsigned char sl_raw[];
@@ -1272,7 +1272,7 @@ static int finish_packed_vocab(nvtb_vocab* v, uint64_t* sorted, int64_t n, int64
       slice_scan_kernel<<<1, kSlThreads, 2 * 4 * P, st>>>(meta, P, meta + P, meta + 2 * P + 1);
       NVTB_LAUNCH_OK();
       const int64_t tiles = (n_keep + kSlTile - 1) / kSlTile;
-      slice_scatter_kernel<<<(int)std::min<int64_t>(tiles, sms), kSlThreads, kSlTile * 8 + 2 * 4 * P, st>>>(
+      slice_scatter_kernel<<<(int)std::min<int64_t>(tiles, 2 * sms), kSlThreads, kSlTile * 8 + 2 * 4 * P, st>>>(
           sorted, n_keep, bmask, lg_slice, P, meta + 2 * P + 1, items);
       NVTB_LAUNCH_OK();
       slice_build_kernel<<<P, 1024, 0, st>>>(items, meta + P, reinterpret_cast<unsigned long long*>(v->t.slots), bmask, lg_slice);

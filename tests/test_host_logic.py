@@ -294,3 +294,104 @@ def test_parquet_dataset_roundtrip_without_pandas_upcast(tmp_path):
     assert back.npartitions == 3
     _frames_equal(back.to_ddf().compute(), tbl.to_pandas())
     assert pq.read_table(os.path.join(out_dir, "part_0.parquet")).schema.field("C1").type == pa.int32()
+
+
+# ------------------------------------------------------------------ round 2: artefact + save/load host logic
+def test_fast_parquet_writer_roundtrips_like_pandas(tmp_path):
+    """unique.<col>.parquet is written with pyarrow directly (no pandas conversion, no dictionary
+    pages); pandas must read back exactly what DataFrame.to_parquet would have produced: the
+    RangeIndex that carries the labels (categorify.py:745-760) and the column dtypes."""
+    import numpy as np
+    import pandas as pd
+    from nvtabular_b200.ops.categorify import _write_numeric_parquet
+    keys = np.array([40, 7, 19, -3], dtype=np.int32)
+    sizes = np.array([9, 4, 4, 1], dtype=np.int64)
+    _write_numeric_parquet(str(tmp_path / "unique.C1.parquet"), {"C1": keys, "C1_size": sizes}, index_start=3)
+    got = pd.read_parquet(tmp_path / "unique.C1.parquet")
+    exp = pd.DataFrame({"C1": keys, "C1_size": sizes})
+    exp.index = pd.RangeIndex(3, 7)
+    pd.testing.assert_frame_equal(got, exp)
+    assert isinstance(got.index, pd.RangeIndex) and got.index.start == 3
+
+
+def test_stat_file_key_columns_keep_their_dtype_with_a_null_row(tmp_path):
+    """cat_stats files carry the null group as a null KEY: int keys must come back as (nullable)
+    ints, not float64 — a reloaded table otherwise sits in another key space than the column"""
+    import numpy as np
+    import pandas as pd
+    from nvtabular_b200.ops._tables import key_columns
+    from nvtabular_b200.ops.keyspace import KeySpace
+    cols = key_columns(KeySpace("int", None, np.dtype("int32")), ["u"], np.array([5, 3, 9]), with_null_row=True)
+    df = pd.DataFrame(cols)
+    df["u_count"] = [2, 1, 1, 0]
+    df.to_parquet(tmp_path / "cat_stats.u.parquet")
+    back = pd.read_parquet(tmp_path / "cat_stats.u.parquet")
+    assert str(back["u"].dtype) == "Int32" and back["u"].isna().tolist() == [False, False, False, True]
+    assert back["u"].dropna().astype("int32").tolist() == [5, 3, 9]
+    fl = key_columns(KeySpace("float", None, np.dtype("float64")), ["x"],
+                     np.array([0, 4607182418800017408], dtype=np.int64), with_null_row=True)   # keys of 0.0, 1.0
+    assert fl["x"].dtype == np.float64 and np.isnan(fl["x"].iloc[-1])
+
+
+def test_graph_json_roundtrip_of_stateless_and_float_state_ops(tmp_path):
+    """Workflow.save / Workflow.load (reference layout: workflow.py:256-348, graph_serializer.py:
+    1077-1165) for the operators whose fitted state is plain floats — no device needed: DAG shape,
+    selectors with multi-column groups, operator parameters and the restored statistics."""
+    import json
+    import nvtabular_b200 as nvt
+    ops = nvt.ops
+    norm = ops.Normalize(out_dtype="float32")
+    norm.means, norm.stds = {"x": 1.5, "y": -2.0}, {"x": 0.5, "y": 4.0}
+    mm = ops.NormalizeMinMax()
+    mm.mins, mm.maxs = {"z": 0.0}, {"z": 10.0}
+    graph = (["x", "y"] >> ops.FillMissing(fill_val=7) >> norm) + (["z"] >> mm) + \
+        (["w"] >> ops.Clip(min_value=0, max_value=9) >> ops.LogOp()) + (["k"] >> ops.HashBucket(13)) + ["label"]
+    wf = nvt.Workflow(graph)
+    wf.save(str(tmp_path / "wf"))
+    meta = json.load(open(tmp_path / "wf" / "metadata.json"))
+    assert "nvtabular" in meta["versions"] and "generated_timestamp" in meta
+    g = json.load(open(tmp_path / "wf" / "graph.json"))
+    assert g["format_version"] == 1
+    by_class = {}
+    for n in g["nodes"]:
+        by_class.setdefault(n["op_class"], []).append(n)
+    assert by_class["nvtabular.ops.normalize.Normalize"][0]["op_state"]["means"] == {"x": 1.5, "y": -2.0}
+    assert by_class["nvtabular.ops.clip.Clip"][0]["op_params"] == {"min_value": 0, "max_value": 9}
+    assert "merlin.dag.ops.concat_columns.ConcatColumns" in by_class and "merlin.dag.ops.selection.SelectionOp" in by_class
+    ids = {n["id"] for n in g["nodes"]}
+    assert all(set(n["parent_ids"]) <= ids for n in g["nodes"]) and g["output_node_id"] in ids
+    wf2 = nvt.Workflow.load(str(tmp_path / "wf"))
+    order = wf2.output_node.topo_order()
+    kinds = [n.kind for n in order]
+    assert kinds.count("input") == 5 and kinds.count("concat") >= 1
+    ops2 = {type(n.op).__name__: n.op for n in order if n.kind == "op"}
+    assert ops2["Normalize"].means == {"x": 1.5, "y": -2.0} and ops2["Normalize"].stds == {"x": 0.5, "y": 4.0}
+    assert str(ops2["Normalize"].out_dtype) == "float32"
+    assert ops2["NormalizeMinMax"].maxs == {"z": 10.0} and ops2["FillMissing"].fill_val == 7
+    assert ops2["Clip"].min_value == 0 and ops2["Clip"].max_value == 9 and ops2["HashBucket"].num_buckets == 13
+    assert sorted(wf2.output_node.output_columns.names) == ["k", "label", "w", "x", "y", "z"]
+    with pytest.raises(nvt.serialize.WorkflowSerializationError):
+        bad = dict(g)
+        bad["format_version"] = 99
+        json.dump(bad, open(tmp_path / "wf" / "graph.json", "w"))
+        nvt.Workflow.load(str(tmp_path / "wf"))
+
+
+def test_operator_hooks_without_device():
+    """compute_selector / supported_formats / inference_initialize contracts (categorify.py:589-609)"""
+    import warnings
+    import nvtabular_b200 as nvt
+    from nvtabular_b200.graph import ColumnSchema, Schema
+    from nvtabular_b200.inference import DataFormats
+    op = nvt.ops.Normalize()
+    sel = nvt.ColumnSelector(["a", "b"])
+    assert op.compute_selector(Schema([ColumnSchema("a"), ColumnSchema("b")]), sel, sel, None) is sel
+    with pytest.raises(ValueError):
+        op.compute_selector(Schema([ColumnSchema("a")]), sel, sel, None)
+    assert op.supported_formats & DataFormats.NUMPY_DICT_ARRAY and op.supported_formats & DataFormats.PANDAS_DATAFRAME
+    assert nvt.ops.HashBucket(3).supported_formats & DataFormats.PANDAS_DATAFRAME
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert nvt.ops.Categorify(encode_type="combo").inference_initialize(sel, {}) is None
+        assert any("combo" in str(x.message) for x in w)
+    assert nvt.ops.FillMissing(add_binary_cols=True).inference_initialize(sel, {}) is None

@@ -31,29 +31,48 @@ def family(name):
     return "other"
 
 
-def main(path):
+_B = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def main(path, traffic=None):
+    """traffic = (fits, calls_per_fit, rows_per_gpu): also print the DRAM bytes per hashagg_insert call"""
     lines = [ln for ln in open(path) if not ln.startswith("==")]
-    agg, fam = collections.OrderedDict(), collections.Counter()
+    agg, fam, fam_bytes = collections.OrderedDict(), collections.Counter(), collections.Counter()
     for r in csv.DictReader(lines):
         name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("nvtb::", "")
         if "at::" in name or name.startswith("cub::") or "elementwise" in name:
             continue                                   # torch's data-generation kernels: outside the step
         v = float(r["Metric Value"].replace(",", ""))
         u = r["Metric Unit"]
+        if r["Metric Name"].startswith("dram__bytes"):
+            d = agg.setdefault(name[:70], [0, 0.0, 0.0])
+            d[2] += v * _B.get(u, 1.0)
+            fam_bytes[family(name)] += v * _B.get(u, 1.0)
+            continue
         us = v / 1e3 if u in ("ns", "nsecond") else v * 1e3 if u in ("ms", "msecond") else v * 1e6 if u in ("s", "second") else v
-        d = agg.setdefault(name[:70], [0, 0.0])
+        d = agg.setdefault(name[:70], [0, 0.0, 0.0])
         d[0] += 1
         d[1] += us
         fam[family(name)] += us
     tot = sum(v[1] for v in agg.values())
+    if traffic:
+        import json
+        fits, calls, rows = traffic
+        b = (fam_bytes["hashagg_insert"] + 0.0) / fits / calls
+        print(json.dumps({"criteo": {"hashagg_insert": {"rows_per_gpu": rows, "dram_bytes_per_launch": b,
+                                                        "how": f"DRAM read+write bytes of the family's kernels over {fits} fits / {calls} calls per fit"}}}))
+        return
     print(f"engine kernels: {sum(v[0] for v in agg.values())} launches, {tot / 1e3:.1f} ms under ncu (cold cache, serialised)\n")
     print("| family | ms | share |\n|---|---:|---:|")
     for k, v in fam.most_common():
         print(f"| {k} | {v / 1e3:.1f} | {100 * v / tot:.1f} % |")
-    print("\n| kernel | family | launches | total ms | share | avg us |\n|---|---|---:|---:|---:|---:|")
-    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"| `{k}` | {family(k)} | {n} | {t / 1e3:.2f} | {100 * t / tot:.1f} % | {t / n:.1f} |")
+    print("\n| kernel | family | launches | total ms | share | avg us | DRAM GB (rd+wr) |\n|---|---|---:|---:|---:|---:|---:|")
+    for k, (n, t, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{k}` | {family(k)} | {n} | {t / 1e3:.2f} | {100 * t / tot:.1f} % | {t / max(n, 1):.1f} | {b / 1e9:.2f} |")
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) > 2 and sys.argv[2] == "--traffic":
+        main(sys.argv[1], (int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])))
+    else:
+        main(sys.argv[1])
