@@ -246,10 +246,13 @@ def run_step_e2e(nvt, wf, host_parts, out_host, fit=True):
 # =======================================================================================
 # CPU reference (oracle port): bounded samples of the same workloads
 # =======================================================================================
-def cpu_reference(workload, rows, workers, profile_rows, steps=1, warmup=0):
+def cpu_reference(workload, rows, workers, profile_rows, steps=1, warmup=0, budget_s=None):
     """The reference's CPU path (oracle/parallel.py) on a bounded sample of the same synthetic
-    workload, generated with the same generator code on the CPU.  -> (rows/s, seconds per step,
-    steps actually run)"""
+    workload, generated with the same generator code on the CPU.  With `budget_s` the sample is
+    SIZED so that warmup + steps passes fit the budget: a calibration pass over the first 2^18 rows
+    gives the rate, the sample is the first min(rows, rate x budget per step / 2) rows (the /2
+    covers the super-linear merge of the partials).  -> (rows/s, seconds per step, steps run,
+    rows per step)"""
     from nvtabular_b200 import synth
     if workload == "criteo":
         from oracle.parallel import run_criteo_workflow
@@ -258,31 +261,37 @@ def cpu_reference(workload, rows, workers, profile_rows, steps=1, warmup=0):
         # what pandas itself holds for a nullable int column read from parquet: float64 + NaN
         df = df.astype({c: "float64" for c in synth.CAT_NAMES + synth.CONT_NAMES})
 
-        def once():
-            tf, tt, *_ = run_criteo_workflow(df, synth.CAT_NAMES, synth.CONT_NAMES, workers)
+        def once(n):
+            tf, tt, *_ = run_criteo_workflow(df.iloc[:n], synth.CAT_NAMES, synth.CONT_NAMES, workers)
             return tf + tt
     elif workload == "hashbucket":
         from oracle.parallel import run_hashbucket
         frame = synth.hashbucket_frame(rows, 40, device="cpu")
         cols = [frame[c].data.numpy() for c in frame.columns]
 
-        def once():
-            return run_hashbucket(cols, 1 << 20, workers)
+        def once(n):
+            return run_hashbucket([c[:n] for c in cols], 1 << 20, workers)
     else:
         from oracle.parallel import run_movielens_workflow
         frame = synth.movielens_frame(rows, device="cpu")
         df = frame.to_pandas()
 
-        def once():
-            tf, tt = run_movielens_workflow(df, workers)
+        def once(n):
+            tf, tt = run_movielens_workflow(df.iloc[:n].reset_index(drop=True), workers)
             return tf + tt
+    n_step = rows
+    if budget_s is not None:
+        n_cal = min(rows, 1 << 18)
+        t_cal = max(once(n_cal), 1e-3)
+        per_step = budget_s / max(1, steps + warmup)
+        n_step = int(min(rows, max(n_cal, (n_cal / t_cal) * per_step * 0.5)))
     times = []
     for i in range(warmup + steps):
-        t = once()
+        t = once(n_step)
         if i >= warmup:
             times.append(t)
     sec = sum(times) / len(times)
-    return rows / sec, sec, len(times)
+    return n_step / sec, sec, len(times), n_step
 
 
 CPU_SAMPLE_ROWS = {"criteo": (1 << 20, 1 << 22), "hashbucket": (1 << 20, 1 << 23), "movielens": (1 << 20, 1 << 23)}
@@ -544,8 +553,8 @@ def main():
             return 0
         cores = os.cpu_count() or 1
         cpu_rows = args.cpu_rows or CPU_SAMPLE_ROWS[wl][1]
-        value, sec, ran = cpu_reference(wl, cpu_rows, cores, args.profile_rows, steps=max(1, args.steps),
-                                        warmup=args.warmup)
+        value, sec, ran, cpu_rows = cpu_reference(wl, cpu_rows, cores, args.profile_rows, steps=max(1, args.steps),
+                                                  warmup=args.warmup, budget_s=float(os.environ.get("NVTB_REF_BUDGET_S", "150")))
         line = {
             "impl": "reference", "metric": METRIC[wl], "value": value, "unit": "rows/s", "n_gpus": args.gpus,
             "steps": ran, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
@@ -553,8 +562,10 @@ def main():
             "data": "synthetic", "config": workload_config(args, world, rows),
             "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "cpu_model": _cpu_model(),
                              "kind": "port",
-                             "sample": f"each step = fit+transform of {cpu_rows} rows of the same synthetic table "
-                                       f"(same generator, same cardinality profile), partition-parallel over "
+                             "sample": f"each step = {'fit+transform' if wl != 'hashbucket' else 'transform'} of the first "
+                                       f"{cpu_rows} rows of the same synthetic table (same generator, same cardinality "
+                                       f"profile; sized by a calibration pass so that warmup + steps fit "
+                                       f"~{os.environ.get('NVTB_REF_BUDGET_S', '150')} s), partition-parallel over "
                                        f"{cores} processes (oracle/parallel.py); {sec:.2f} s per step"},
             "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -775,7 +786,7 @@ def main():
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cpu_rows = args.cpu_rows or CPU_SAMPLE_ROWS[wl][0]
-        v, sec, _ = cpu_reference(wl, cpu_rows, 1, args.profile_rows)
+        v, sec, _, cpu_rows = cpu_reference(wl, cpu_rows, 1, args.profile_rows, budget_s=20.0)
         cpu_baseline = {"value": v, "unit": "rows/s", "cores": 1, "cpu_model": _cpu_model(), "kind": "port",
                         "sample": f"{cpu_rows} rows of the same synthetic table, "
                                   f"{'fit+transform' if has_fit else 'transform'}, {sec:.1f} s on 1 core "

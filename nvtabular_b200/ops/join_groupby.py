@@ -125,7 +125,7 @@ def build_group_table(name, key_names, space, agg: engine.HashAgg, cont_names, s
     # "count" is pandas count() of the FIRST key column (categorify.py:989-999):
     # == size when that component is non-null, 0 otherwise
     if isinstance(space, ComboKeySpace):
-        fn = torch.from_numpy(space.first_component_null(keys.cpu().numpy())).to(dev) if U else \
+        fn = space.first_component_null_t(keys) if U else \
             torch.zeros(0, dtype=torch.bool, device=dev)
         count = torch.where(fn, torch.zeros_like(sizes_f), sizes_f)
     else:

@@ -326,6 +326,14 @@ class ComboKeySpace:
         vals[(r <= 0)] = None
         return vals
 
+    def first_component_null_t(self, keys: torch.Tensor) -> torch.Tensor:
+        """device version of first_component_null for packed two-component keys (no host round trip
+        over tens of millions of group keys); falls back to the host path for deeper combinations"""
+        if len(self.spaces) == 2 or self.direct:
+            a = keys >> 32                                        # arithmetic: the first component, sign-extended
+            return (a == int(_I32_MIN)) if self.direct else (a <= 0)
+        return torch.from_numpy(self.first_component_null(keys.cpu().numpy())).to(keys.device)
+
     def first_component_null(self, keys: np.ndarray) -> np.ndarray:
         a, _ = engine.unpack_keys2(keys) if len(self.spaces) == 2 or self.direct else (None, None)
         if a is None:

@@ -146,7 +146,7 @@ class TargetEncoding(StatOperator):
         g.all_vocab = engine.Vocab.from_arrays(keys)
         sizes_f = sizes.to(torch.float64)
         if isinstance(space, ComboKeySpace) and U:
-            fn = torch.from_numpy(space.first_component_null(keys.cpu().numpy())).to(dev)
+            fn = space.first_component_null_t(keys)
             count_all = torch.where(fn, torch.zeros_like(sizes_f), sizes_f)
         else:
             count_all = sizes_f
@@ -183,11 +183,11 @@ class TargetEncoding(StatOperator):
         ym = torch.tensor([float(y_mean[t]) for t in targets], dtype=torch.float64, device=keys.device)
         if self.kfold > 1:
             fk, count_f, sum_f = g._fold
-            a, gid = engine.unpack_keys2(fk.cpu().numpy())
-            gid_t = torch.from_numpy(gid.astype(np.int64)).to(fk.device)
+            # second component of the packed (fold, group id) key, on the device (engine.unpack_keys2:
+            # b = low word ^ 2^31; group ids are >= 0, so the unsigned value is the id)
+            gid_t = (fk & 0xFFFFFFFF) ^ 0x80000000
             te = (sum_all[gid_t] - sum_f + p * ym) / ((count_all[gid_t] - count_f)[:, None] + p)
             g.handle = engine.GroupStats(fk, te, -1)
-            g.fold_keys = (a, gid)
             self.stats.setdefault(_make_name(self.fold_name, *g.names, sep=self.name_sep), name)
         else:
             te = (sum_all + p * ym) / (count_all[:, None] + p)
@@ -232,7 +232,7 @@ class TargetEncoding(StatOperator):
         if self.kfold > 1:
             fname = _make_name(self.fold_name, *g.names, sep=self.name_sep)
             fk, count_f, sum_f = g._fold
-            a, gid = g.fold_keys
+            a, gid = engine.unpack_keys2(fk.cpu().numpy())      # host copies only when the file is written
             kk = np.concatenate([k, np.zeros(1, dtype=k.dtype)])        # row U = the null group
             fdata = {self.fold_name: a.astype(np.int64)}
             cols = key_columns(g.space, g.names, kk[gid.astype(np.int64)])
