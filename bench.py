@@ -300,7 +300,8 @@ CPU_SAMPLE_ROWS = {"criteo": (1 << 20, 1 << 22), "hashbucket": (1 << 20, 1 << 23
 def workload_config(args, world, rows):
     total = rows * world
     if args.workload == "criteo":
-        return {"workload": "BASELINE.json configs[1]: Criteo-1TB-shaped synthetic (13 int + 26 cat int32, "
+        which = "configs[1]" if world == 1 else f"configs[2] (the configs[1] workflow sharded over {world} B200s)"
+        return {"workload": f"BASELINE.json {which}: Criteo-1TB-shaped synthetic (13 int + 26 cat int32, "
                             "nullable), Categorify+FillMissing+Normalize, one step = Workflow.fit + "
                             "Workflow.transform over the HBM-resident table",
                 "rows_per_gpu": rows, "total_rows": total, "partitions_per_gpu": args.parts,
@@ -312,7 +313,9 @@ def workload_config(args, world, rows):
                                        "every vocabulary up to 2^20 keys written inside fit (under the GPU's "
                                        "builds of the large vocabularies); larger vocabulary files on first read",
                               "lazy": "deferred until read"}[args.artifacts],
-                "parallelism": f"row-sharded x{world}, key-hash owner merge over NCCL" if world > 1 else "single GPU"}
+                "parallelism": (f"row-sharded x{world}; NCCL: moments all-reduce, key-hash owner merge (small "
+                                f"columns), key-range exchange of sorted pairs + shard all-gather (large columns)")
+                if world > 1 else "single GPU"}
     if args.workload == "hashbucket":
         return {"workload": "BASELINE.json configs[4]: 40 int64 key columns, keys uniform over 1e8 ids through a "
                             "64-bit bijection, HashBucket(num_buckets=2**20), one step = Workflow.transform over "

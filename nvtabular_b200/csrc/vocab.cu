@@ -10,7 +10,7 @@
 // Ordering rule: (size desc, key asc) — the stable form of the reference's
 // sort_values(key) followed by sort_values(size, ascending=False)
 // (categorify.py:1300,1316).  Implemented as two stable LSD
-// radix sorts (cub::DeviceRadixSort — library code, on U distinct keys, not on
+// radix sorts (hand-written passes of radix.cuh for int32 keys; cub::DeviceRadixSort - library code - only for 64-bit keys; on U distinct keys, not on
 // the N-row stream).  The encode is a single in-order probe pass: no join, no
 // sort back to row order.
 #include <algorithm>
@@ -1038,11 +1038,23 @@ static int vocab_post(nvtb_vocab* v, cudaStream_t st) {
   return NVTB_OK;
 }
 
+// (key, size) rows -> packed pairs (key ^ 2^31) << 32 | size (int32-valued keys, sizes < 2^32)
+__global__ void __launch_bounds__(kThreads)
+pack_pairs_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sizes, int64_t n,
+                  uint64_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = ((uint64_t)((uint32_t)(int32_t)keys[i] ^ 0x80000000u) << 32) | (uint64_t)(uint32_t)sizes[i];
+}
+
 }  // namespace nvtb
 
 using namespace nvtb;
 
 extern "C" {
+
+static int finish_packed_vocab(nvtb_vocab* v, uint64_t* sorted, int64_t n, int64_t freq_threshold, int64_t max_size,
+                               int64_t num_buckets, cudaStream_t st);
 
 int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* sizes,
                      int64_t n, int64_t null_size, int64_t freq_threshold,
@@ -1106,32 +1118,40 @@ int nvtb_vocab_build(nvtb_vocab_t** out, const int64_t* keys, const int64_t* siz
       while (size_bits < 63 && ((int64_t)1 << size_bits) <= size_bound) ++size_bits;
     }
     const int g_x = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)sm_count() * 8));
-    if (key32 && size_bound > 0 && size_bound < ((int64_t)1 << 32)) {
-      // both sort keys fit 32 bits: sort (uint32, uint32) pairs - half the bytes per pass
-      uint32_t *a32 = nullptr, *b32 = nullptr, *c32 = nullptr, *d32 = nullptr;
-      NVTB_CUDA_OK(cudaMallocAsync(&a32, sizeof(uint32_t) * n, st));
-      NVTB_CUDA_OK(cudaMallocAsync(&b32, sizeof(uint32_t) * n, st));
-      NVTB_CUDA_OK(cudaMallocAsync(&c32, sizeof(uint32_t) * n, st));
-      NVTB_CUDA_OK(cudaMallocAsync(&d32, sizeof(uint32_t) * n, st));
-      pack32_kernel<<<g_x, kThreads, 0, st>>>(keys, sizes, n, a32, c32);
-      NVTB_LAUNCH_OK();
-      size_t ta = 0, tb = 0;
-      NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, ta, a32, b32, c32, d32, n, 0, 32, st));
-      NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, d32, c32, b32, a32, n, 0, size_bits, st));
-      size_t tbytes = std::max(ta, tb);
-      void* tmp32 = nullptr;
-      NVTB_CUDA_OK(cudaMallocAsync(&tmp32, tbytes ? tbytes : 1, st));
-      NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp32, tbytes, a32, b32, c32, d32, n, 0, 32, st));
-      NVTB_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(tmp32, tbytes, d32, c32, b32, a32, n, 0, size_bits, st));
-      unpack32_kernel<<<g_x, kThreads, 0, st>>>(a32, c32, n, k2, s2);
-      NVTB_LAUNCH_OK();
-      NVTB_CUDA_OK(cudaFreeAsync(a32, st));
-      NVTB_CUDA_OK(cudaFreeAsync(b32, st));
-      NVTB_CUDA_OK(cudaFreeAsync(c32, st));
-      NVTB_CUDA_OK(cudaFreeAsync(d32, st));
-      NVTB_CUDA_OK(cudaFreeAsync(tmp32, st));
+    if (key32 && size_bound > 0 && size_bound < ((int64_t)1 << 32) && n < (int64_t)0x7FFFFFF0 &&
+        !(getenv("NVTB_VOCAB_SORT") && strcmp(getenv("NVTB_VOCAB_SORT"), "cub") == 0)) {
+      // int32 keys, counts below 2^32 (every Categorify column of the Criteo workload): the rows
+      // become packed pairs (key ^ 2^31) << 32 | size and the order (size desc, key asc) is two runs
+      // of the hand-written stable radix passes (radix.cuh) over the bits that can differ — key
+      // bits ascending, then size bits descending — followed by the same tail as the sorted
+      // accumulators (cut, meta sums, narrow lookup).  No library sort on this path.
       NVTB_CUDA_OK(cudaFreeAsync(k1, st));
       NVTB_CUDA_OK(cudaFreeAsync(s1, st));
+      NVTB_CUDA_OK(cudaFreeAsync(k2, st));
+      NVTB_CUDA_OK(cudaFreeAsync(s2, st));
+      uint64_t *p0 = nullptr, *p1 = nullptr;
+      void* scratch = nullptr;
+      NVTB_CUDA_OK(cudaMallocAsync(&p0, sizeof(uint64_t) * n, st));
+      NVTB_CUDA_OK(cudaMallocAsync(&p1, sizeof(uint64_t) * n, st));
+      NVTB_CUDA_OK(cudaMallocAsync(&scratch, rx_scratch_bytes<uint64_t>(n, kRxMaxStableBits), st));
+      NVTB_CUDA_OK(cudaMemsetAsync(scratch, 0, 256, st));
+      pack_pairs_kernel<<<g_x, kThreads, 0, st>>>(keys, sizes, n, p0);
+      NVTB_LAUNCH_OK();
+      int in_b = 0;
+      int rc = rx_sort_bits<uint64_t>(p0, p1, nullptr, n, 32, 64, false, scratch, st, &in_b);
+      if (rc) return rc;
+      uint64_t* cur = in_b ? p1 : p0;
+      uint64_t* oth = in_b ? p0 : p1;
+      int in_o = 0;
+      rc = rx_sort_bits<uint64_t>(cur, oth, nullptr, n, 0, size_bits > 32 ? 32 : size_bits, true, scratch, st, &in_o);
+      if (rc) return rc;
+      uint64_t* sorted = in_o ? oth : cur;
+      NVTB_CUDA_OK(cudaFreeAsync(in_o ? cur : oth, st));
+      NVTB_CUDA_OK(cudaFreeAsync(scratch, st));
+      rc = finish_packed_vocab(v, sorted, n, freq_threshold, max_size, num_buckets, st);
+      if (rc) { nvtb_vocab_destroy(v); return rc; }
+      *out = v;
+      return NVTB_OK;
     } else {
     const int64_t* sort_in = keys;
     if (key32) {
