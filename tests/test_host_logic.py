@@ -395,3 +395,24 @@ def test_operator_hooks_without_device():
         assert nvt.ops.Categorify(encode_type="combo").inference_initialize(sel, {}) is None
         assert any("combo" in str(x.message) for x in w)
     assert nvt.ops.FillMissing(add_binary_cols=True).inference_initialize(sel, {}) is None
+
+
+def test_reference_arm_under_torchrun_prints_one_line(tmp_path):
+    """The driver launches `bench.py --impl reference --gpus N` the way it launches the GPU arm
+    (torchrun, N ranks): rank 0 alone runs the CPU path and prints ONE JSON line with the contract's
+    keys; the other ranks exit 0 without work."""
+    import json
+    port = 29700 + os.getpid() % 200
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+           "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-rows", "60000"]
+    env = dict(os.environ, NVTB_REF_BUDGET_S="20")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 1 and d["higher_is_better"] is True
+    assert d["unit"] == "rows/s" and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "cpu_model" in d["cpu_baseline"]
+    assert d["config"]["total_rows"] == 2 * d["config"]["rows_per_gpu"] and "configs[2]" in d["config"]["workload"]
