@@ -54,3 +54,29 @@ def test_owner_exchange_two_ranks_gloo(tmp_path):
         assert res[0]["sorted"][c]["keys"] == exp["k"].tolist()
         assert res[0]["sorted"][c]["sizes"] == exp["s"].tolist()
         assert res[0]["sorted"][c]["null"] == 2 * (3 + c) + 1
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("world", [3, 4])
+def test_sorted_exchange_world_sizes(tmp_path, world):
+    """dist.global_merge_sorted on 3 (odd merge tree, one empty shard) and 4 ranks (what the scaling run
+    uses): every rank ends with the union's value_counts in (count desc, key asc) order."""
+    port = 29900 + (os.getpid() + world) % 90
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "dist_sorted_worker.py"), str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    res = [json.load(open(tmp_path / f"rank{i}.json")) for i in range(world)]
+    for i in range(1, world):
+        assert res[i]["sorted"] == res[0]["sorted"]
+    for c in range(3):
+        allk = sum((res[i]["local"][c] for i in range(world)), [])
+        vc = pd.Series(allk).value_counts(sort=False)
+        exp = pd.DataFrame({"k": vc.index.to_numpy(), "s": vc.to_numpy()}).sort_values(
+            ["s", "k"], ascending=[False, True], kind="stable")
+        assert res[0]["sorted"][c]["keys"] == exp["k"].tolist()
+        assert res[0]["sorted"][c]["sizes"] == exp["s"].tolist()
+        assert res[0]["sorted"][c]["null"] == sum(2 + i + c for i in range(world))
