@@ -64,6 +64,47 @@ def _traffic(workload, kernel, rows):
     return None
 
 
+def _host_memory_budget():
+    """bytes of host memory this container may still take: the cgroup limit (v2, then v1) minus its
+    current charge, capped by MemAvailable.  None when nothing can be read."""
+    def _read_int(path):
+        try:
+            v = open(path).read().strip()
+            return None if v == "max" else int(v)
+        except Exception:
+            return None
+    cands = []
+    for lim, cur in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                     ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        limit = _read_int(lim)
+        if limit is not None and limit < (1 << 60):
+            cands.append(limit - (_read_int(cur) or 0))
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                cands.append(int(ln.split()[1]) * 1024)
+    except Exception:
+        pass
+    return min(cands) if cands else None
+
+
+def e2e_rows_within_host_memory(want_rows, bytes_per_row, local_ranks, budget):
+    """The e2e leg pins its inputs AND its results (bytes_per_row of both per row) in every rank of
+    the box; a pinned page is charged to the container, and a container over its limit is killed,
+    not refused.  Keep the ranks' sum below 80 % of `budget`; whole 2^23-row partitions (their pinned
+    buffers are exact powers of two), at least one.  `budget` None = unknown = leave the request."""
+    if budget is None:
+        return want_rows
+    fit = int(budget * 0.8 / max(local_ranks, 1) / bytes_per_row)
+    if fit >= want_rows:
+        return want_rows
+    return max(1 << 23, fit >> 23 << 23)
+
+
+
+E2E_PINNED_BYTES_PER_ROW = 512      # measured: 480.6 (profiles/bench_r2_criteo_1gpu.json: (h2d + d2h) / rows)
+
+
 def _cpu_model():
     try:
         with open("/proc/cpuinfo") as f:
@@ -737,6 +778,15 @@ def main():
             # the 1-GPU box's cgroup holds 200 GiB — partitions of exactly 2^23 rows (32 / 64 MiB
             # buffers) and at most 2^27 rows per GPU keep a step at ~64 GB of pinned memory
             e_rows = args.e2e_rows or min(rows, 1 << 27)
+            if not args.e2e_rows:
+                # 481 B per row of the Criteo table are pinned (inputs + int64/float64 results); the same
+                # bound is applied to the other workloads, whose rows are narrower
+                local = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+                e_rows = e2e_rows_within_host_memory(e_rows, E2E_PINNED_BYTES_PER_ROW, local, _host_memory_budget())
+                if world > 1:
+                    agree = torch.tensor([e_rows], dtype=torch.int64, device=dev)
+                    dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+                    e_rows = int(agree.item())
             e_parts = args.e2e_parts or max(1, (e_rows + (1 << 23) - 1) >> 23)
             src = table.slice_rows(0, e_rows) if e_rows <= rows else make_table(wl, e_rows, dev, rank, args.profile_rows)
             host = host_partitions(src, e_parts)

@@ -416,3 +416,22 @@ def test_reference_arm_under_torchrun_prints_one_line(tmp_path):
     assert d["unit"] == "rows/s" and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "cpu_model" in d["cpu_baseline"]
     assert d["config"]["total_rows"] == 2 * d["config"]["rows_per_gpu"] and "configs[2]" in d["config"]["workload"]
+
+
+def test_bench_e2e_rows_fit_the_host_memory_limit():
+    """bench.py sizes the pinned e2e leg to the container's memory limit: unchanged where the known
+    boxes have room (200 GiB for 1 GPU, 137 GB per GPU beyond), whole 2^23-row partitions and never
+    zero where they do not."""
+    import bench
+    G = 1 << 30
+    want, bpr = 1 << 27, bench.E2E_PINNED_BYTES_PER_ROW
+    assert bench.e2e_rows_within_host_memory(want, bpr, 1, 200 * G) == want
+    assert bench.e2e_rows_within_host_memory(want, bpr, 2, 256 * G) == want
+    assert bench.e2e_rows_within_host_memory(want, bpr, 8, 1024 * G) == want
+    assert bench.e2e_rows_within_host_memory(want, bpr, 1, None) == want
+    small = bench.e2e_rows_within_host_memory(want, bpr, 8, 200 * G)
+    assert small % (1 << 23) == 0 and 0 < small < want
+    assert 8 * small * bpr <= 0.8 * 200 * G
+    assert bench.e2e_rows_within_host_memory(want, bpr, 8, 1 * G) == 1 << 23
+    b = bench._host_memory_budget()
+    assert b is None or b > 0
