@@ -26,6 +26,13 @@
  *     and destroyed explicitly; build-phase calls on one handle must not be
  *     issued concurrently; finalised vocab / groupstats handles are immutable
  *     and may be probed from any number of streams.
+ *   - ONE device per process (the one-process-per-GPU model of SURVEY §8e): the
+ *     hashagg build phase keeps grow-only scratch (two accumulator arenas, the
+ *     partition buffer, the sort / bucket scratch) in process-global pools on the device
+ *     that was current at the first call.  The pools are mutex-guarded and a use
+ *     on another stream waits on an event of the previous one, so build calls
+ *     of DIFFERENT handles may come from different streams of that device; a
+ *     second device in the same process is not supported and not detected.
  */
 #ifndef NVTB200_H
 #define NVTB200_H
