@@ -300,3 +300,79 @@ def test_hash_golden_file():
         got = oracle.hash_values(arr) if dt not in ("float32", "float64") else \
             oracle.hashing._mix(bits)   # raw-bit hash (the oracle maps NaN to the null pattern)
         np.testing.assert_array_equal(got, np.array(case["hash"], dtype=np.uint64), err_msg=dt)
+
+
+# reference tests/unit/ops/test_categorify.py:543-557 (issue 1325: the null row exists with 0 observations)
+def test_categorify_no_nulls():
+    df = pd.DataFrame({"user_id": [1, 2, 3, 4, 6, 8, 5, 3] * 10, "item_id": [2, 4, 4, 7, 5, 2, 5, 2] * 10})
+    o, out = _fit_transform(df, ["user_id", "item_id"])
+    meta = o.categories["user_id"].meta
+    assert meta["kind"].iloc[1] == "null" and meta["num_observed"].iloc[1] == 0
+    # pad, null and oov rows precede the uniques: the most frequent user (3) gets the first free index
+    assert out["user_id"].min() == 3 and set(out.loc[df["user_id"] == 3, "user_id"]) == {3}
+
+
+# reference tests/unit/ops/test_categorify.py:615-634
+def test_categorify_max_size_null_iloc_check():
+    df = pd.DataFrame({"C1": [1, np.nan, 3, 4, 3] * 5, "C2": [1, 1, 2, 3, 6] * 5})
+    o, _ = _fit_transform(df, ["C1", "C2"], max_size=4)
+    m1, m2 = o.categories["C1"].meta, o.categories["C2"].meta
+    assert m1["kind"].iloc[1] == "null" and m1["num_observed"].iloc[1] == 5
+    assert m2["kind"].iloc[1] == "null" and m2["num_observed"].iloc[1] == 0
+
+
+# reference tests/unit/ops/test_target_encode.py:37-84: with unique categories the per-fold stat
+# table holds exactly the (fold, key) pairs of the transformed rows
+@pytest.mark.parametrize("cat_groups", ["Author", [["Author", "Engaging-User"]]])
+@pytest.mark.parametrize("kfold", [1, 3])
+@pytest.mark.parametrize("fold_seed", [None, 42])
+def test_target_encode_fold_mapping(cat_groups, kfold, fold_seed):
+    import string
+    from oracle.groupby import add_fold
+    df = pd.DataFrame({"Author": list(string.ascii_uppercase), "Engaging-User": list(string.ascii_lowercase),
+                       "Cost": range(26), "Post": [0, 1] * 13})
+    parts = [df.iloc[:9], df.iloc[9:18], df.iloc[18:]]
+    groups = [cat_groups] if isinstance(cat_groups, str) else cat_groups
+    outs, tables, y_mean = target_encoding(parts, groups, ["Cost"], kfold=kfold, fold_seed=fold_seed,
+                                           out_dtype="float32")
+    out = pd.concat(outs)
+    assert len(out) == 26 and out.dtypes.iloc[0] == np.float32
+    assert math.isclose(y_mean["Cost"], 12.5)
+    if kfold > 1:
+        g = [cat_groups] if isinstance(cat_groups, str) else cat_groups[0]
+        cols = ["__fold__"] + g
+        check = tables["_".join(cols)][cols].sort_values(cols).reset_index(drop=True)
+        folded = pd.concat([p.assign(__fold__=add_fold(len(p), kfold, fold_seed)) for p in parts])
+        got = folded[cols].sort_values(cols).reset_index(drop=True)
+        pd.testing.assert_frame_equal(check, got, check_dtype=False)
+        # every key is alone in its group: the out-of-fold estimate is the smoothed prior
+        np.testing.assert_allclose(out.iloc[:, 0].values, 12.5, rtol=1e-6)
+    else:
+        te = out.iloc[:, 0].values
+        np.testing.assert_allclose(te, (df["Cost"].values + 20 * 12.5) / 21.0, rtol=1e-6)
+
+
+# reference tests/unit/ops/test_target_encode.py:87-110 (kfold=1; values from the op's formula
+# target_encoding.py:376-380: (sum + p_smooth * mean) / (count + p_smooth))
+def test_target_encode_group():
+    df = pd.DataFrame({"Cost": range(15), "Post": [1, 2, 3, 4, 5] * 3,
+                       "Author": ["A"] * 5 + ["B"] * 5 + ["C"] * 2 + ["D"] * 3,
+                       "Engaging_User": ["A"] * 5 + ["B"] * 3 + ["E"] * 2 + ["D"] * 3 + ["G"] * 2})
+    df["label"] = (df["Post"] > 3).astype("int8")
+    outs, _, y_mean = target_encoding([df], ["Author", "Engaging_User"], ["label"], kfold=1, out_dtype="float32")
+    out = outs[0]
+    assert math.isclose(y_mean["label"], 0.4)
+    exp = {"A": (2 + 8.0) / 25, "B": (2 + 8.0) / 25, "C": (0 + 8.0) / 22, "D": (2 + 8.0) / 23}
+    np.testing.assert_allclose(out["TE_Author_label"].values, df["Author"].map(exp).values, rtol=1e-6)
+    exp_u = {"A": 10.0 / 25, "B": (0 + 8.0) / 23, "E": (2 + 8.0) / 22, "D": (0 + 8.0) / 23, "G": (2 + 8.0) / 22}
+    np.testing.assert_allclose(out["TE_Engaging_User_label"].values, df["Engaging_User"].map(exp_u).values, rtol=1e-6)
+
+
+# reference tests/unit/ops/test_hash_bucket.py:36-57: buckets in range, deterministic
+def test_hash_bucket_range_and_determinism():
+    rng = np.random.RandomState(5)
+    v = rng.randint(-2**62, 2**62, 10000)
+    b = oracle.hash_bucket(v, 10)
+    assert b.min() >= 0 and b.max() <= 9 and len(np.unique(b)) == 10
+    np.testing.assert_array_equal(b, oracle.hash_bucket(v.copy(), 10))
+    np.testing.assert_array_equal(b, (pd.util.hash_array(v) % np.uint64(10)).astype(b.dtype))
