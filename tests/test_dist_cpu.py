@@ -59,9 +59,9 @@ def test_owner_exchange_two_ranks_gloo(tmp_path):
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("world", [3, 4])
+@pytest.mark.parametrize("world", [3, 4, 8])
 def test_sorted_exchange_world_sizes(tmp_path, world):
-    """dist.global_merge_sorted on 3 (odd merge tree, one empty shard) and 4 ranks (what the scaling run
+    """dist.global_merge_sorted on 3 (odd merge tree, one empty shard) 4 and 8 ranks (what the scaling run
     uses): every rank ends with the union's value_counts in (count desc, key asc) order."""
     port = 29900 + (os.getpid() + world) % 90
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
